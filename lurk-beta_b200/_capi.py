@@ -1,0 +1,83 @@
+"""ctypes binding of liblurk_b200.so (C ABI: include/lurk_b200.h).  No CPU fallback: if the CUDA library is
+missing or no GPU is present, calls raise."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblurk_b200.so")
+
+FIELD_BN254_FR, FIELD_BN254_FQ, FIELD_PALLAS_FQ, FIELD_PALLAS_FP = 0, 1, 2, 3
+CURVE_BN254_G1, CURVE_GRUMPKIN, CURVE_PALLAS, CURVE_VESTA = 0, 1, 2, 3
+FMT_CANONICAL, FMT_MONTGOMERY = 0, 1
+OK, ERR_ARG, ERR_CUDA, ERR_OOM, ERR_RANGE, ERR_NOGPU, ERR_ORDER = 0, -1, -2, -3, -4, -5, -6
+
+
+class LurkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"liblurk_b200 error {code}: {msg}")
+        self.code = code
+
+
+class DagNode(C.Structure):
+    _fields_ = [("kind", C.c_uint8), ("reserved", C.c_uint8), ("tag", C.c_uint16 * 4), ("child", C.c_uint32 * 4)]
+
+
+_vp, _sz, _i = C.c_void_p, C.c_size_t, C.c_int
+# every symbol declared in include/lurk_b200.h: name -> (restype, argtypes)
+PROTOTYPES = {
+    "lurk_last_error": (C.c_char_p, []),
+    "lurk_version": (_i, []),
+    "lurk_device_count": (_i, []),
+    "lurk_field_modulus": (_i, [_i, _vp]),
+    "lurk_poseidon_hash_batch": (_i, [_i, _i, _vp, _sz, _vp]),
+    "lurk_poseidon_hash_batch_mont": (_i, [_i, _i, _vp, _sz, _vp]),
+    "lurk_poseidon_hash_batch_dev": (_i, [_i, _i, _vp, _sz, _vp, _i, _vp]),
+    "lurk_poseidon_constants": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i), _vp, _vp]),
+    "lurk_poseidon_witness_block": (_sz, [_i, _i]),
+    "lurk_poseidon_witness_batch": (_i, [_i, _i, _vp, _sz, _vp, _i]),
+    "lurk_poseidon_witness_batch_dev": (_i, [_i, _i, _vp, _sz, _vp, _i, _vp]),
+    "lurk_bitdecomp_witness_block": (_sz, [_i]),
+    "lurk_bitdecomp_witness_batch": (_i, [_i, _vp, _sz, _vp, _i]),
+    "lurk_bitdecomp_witness_batch_dev": (_i, [_i, _vp, _sz, _vp, _i, _vp]),
+    "lurk_dag_hash": (_i, [_i, _vp, _sz, _vp, _sz, _vp]),
+    "lurk_msm_ctx_create": (_i, [_i, _vp, _sz, _i, C.POINTER(_vp)]),
+    "lurk_msm_ctx_create_dev": (_i, [_i, _vp, _sz, C.POINTER(_vp)]),
+    "lurk_msm_ctx_destroy": (None, [_vp]),
+    "lurk_msm_ctx_run": (_i, [_vp, _vp, _sz, _i, _vp]),
+    "lurk_msm_ctx_run_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),
+    "lurk_msm": (_i, [_i, _vp, _vp, _sz, _i, _vp]),
+    "lurk_point_sum": (_i, [_i, _vp, _sz, _i, _vp]),
+    "lurk_synthetic_bases": (_i, [_i, C.c_uint64, _sz, _i, _vp]),
+    "lurk_axpy_dev": (_i, [_i, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "lurk_spmv_csr_dev": (_i, [_i, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "lurk_cross_term_dev": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "lurk_convert_dev": (_i, [_i, _vp, _sz, _i, _vp, _vp]),
+    "lurk_ntt_dev": (_i, [_i, _vp, _i, _i, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LurkError(ERR_NOGPU, f"{LIB_PATH} not built -- run __graft_entry__.build(); there is no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise LurkError(rc, lib().lurk_last_error().decode())
+    return rc
+
+
+def np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,537 @@
+// K4: Pedersen commitment = Pippenger multi-scalar multiplication on sm_100a.
+//
+// Replaces Arecibo's CommitmentEngineTrait::commit -> DlogGroup::vartime_multiscalar_mul (third-party crate, called
+// from RecursiveSNARK::prove_step; reference call sites src/proof/nova.rs:287,292, src/proof/supernova.rs:231-244).
+// The commitment key is fixed per (rc, Lang) (src/proof/nova.rs:196-216), so it is uploaded once into a context and
+// kept in HBM in Montgomery affine form (64 B / point); every call streams 32 B scalars.
+//
+// Pipeline (all on one stream, no host synchronisation before the final 2 KB read-back):
+//   1. digits+histogram: one thread per scalar; signed c-bit windows (buckets 1..2^(c-1), sign folded into the point);
+//      warp-aggregated atomics (__match_any_sync) so the 0/1-heavy witness vectors do not serialise on
+//      one counter.
+//   2. exclusive scan of the (windows x 2^(c-1)) bucket counts.
+//   3. scatter: point index | sign written at its bucket's next slot (counting sort; order inside a bucket is free
+//      because point addition commutes -- the affine result is canonical).
+//   4. bucket accumulation, the hot kernel: the sorted list is cut into fixed-length segments, one per thread,
+//      independent of the bucket sizes (perfect balance for any scalar distribution).  A thread gathers its bases
+//      with 128-bit loads (next point prefetched during the current addition), adds them in XYZZ coordinates
+//      (8M+2S mixed addition, no inversions) and flushes a bucket sum whenever the bucket id changes.  The first run
+//      of a segment may continue a bucket started by the previous thread: it goes to a (key, point) partial list
+//      which is reduced by the same rule in a few geometrically shrinking passes.
+//   5. per-window running-sum reduction (chunks of buckets in parallel, then one CTA per window).
+//   6. host: Horner combine of the <= 64 window sums and one inversion to affine.
+// Integer-ALU bound: ~10 Montgomery products per (scalar, window); algorithmic traffic 96 B per term.
+#include "common.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <thread>
+
+namespace lurk {
+
+static constexpr uint32_t KEY_NONE = 0xffffffffu;
+
+struct MsmPlan {
+    int c = 0;             // window bits
+    int nwin = 0;          // windows
+    uint32_t nb = 0;       // buckets per window = 2^(c-1)
+    uint32_t total_buckets = 0;
+    uint32_t seg = 0;      // sorted entries per level-1 thread
+    uint32_t t1 = 0;       // level-1 threads = partial slots
+    uint32_t chunk = 0;    // buckets per bucket-reduce thread
+};
+
+static MsmPlan make_plan(size_t n, int scalar_bits) {
+    MsmPlan p;
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) lg++;
+    p.c = std::min(20, std::max(4, lg - 5));
+    p.nwin = scalar_bits / p.c + 1;
+    p.nb = 1u << (p.c - 1);
+    p.total_buckets = p.nb * (uint32_t)p.nwin;
+    size_t cap = n * (size_t)p.nwin;
+    size_t want_threads = (size_t)sm_count() * 1024;
+    size_t seg = (cap + want_threads - 1) / want_threads;
+    p.seg = (uint32_t)std::min<size_t>(32, std::max<size_t>(8, seg));
+    p.t1 = (uint32_t)((cap + p.seg - 1) / p.seg);
+    if (p.t1 == 0) p.t1 = 1;
+    p.chunk = std::min<uint32_t>(16, p.nb);
+    return p;
+}
+
+// ----------------------------------------------------------------------------- kernels
+// unsigned c-bit window starting at `bit` of a 256-bit little-endian integer
+__device__ __forceinline__ uint32_t window_bits(const uint32_t k[8], int bit, int c) {
+    int word = bit >> 5, sh = bit & 31;
+    if (word >= 8) return 0;
+    uint32_t lo = k[word] >> sh;
+    if (sh + c > 32 && word + 1 < 8) lo |= k[word + 1] << (32 - sh);
+    return lo & ((1u << c) - 1);
+}
+
+template <class Fs>
+__global__ void __launch_bounds__(256) msm_count_kernel(const Fs *__restrict__ scalars, size_t n, int fmt, int c, int nwin, uint32_t nb,
+                                                        uint32_t *__restrict__ counts) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    // all lanes walk the windows together so the warp-aggregation below sees converged lanes
+    Fs k = Fs::zero();
+    if (live) { k = load_fe<Fs>(scalars + i); if (fmt == LURK_FMT_MONTGOMERY) k = k.to_canonical(); }
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (c - 1);
+    const uint32_t lane = threadIdx.x & 31;
+    for (int w = 0; w < nwin; w++) {
+        uint32_t raw = window_bits(k.v, w * c, c) + carry;
+        uint32_t neg = raw > half;
+        uint32_t mag = neg ? (1u << c) - raw : raw;
+        carry = neg;
+        uint32_t key = (live && mag) ? (uint32_t)w * nb + (mag - 1) : KEY_NONE;
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (key != KEY_NONE && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(counts + key, (uint32_t)__popc(peers));
+    }
+}
+
+// single-CTA exclusive scan: offsets[0..len] (offsets[len] = total)
+__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t *__restrict__ counts, uint32_t len, uint32_t *__restrict__ offsets) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t per = (len + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = tid * per, e = min(b + per, len);
+    uint32_t sum = 0;
+    for (uint32_t i = b; i < e; i++) sum += counts[i];
+    uint32_t incl = sum;
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = warp_sums[lane], wi = ws;
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= (uint32_t)d) wi += t; }
+        warp_sums[lane] = wi - ws;
+        if (lane == 31) carry_s = wi;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[wid] + incl - sum;
+    for (uint32_t i = b; i < e; i++) { offsets[i] = run; run += counts[i]; }
+    if (tid == 0) offsets[len] = carry_s;
+}
+
+template <class Fs>
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const Fs *__restrict__ scalars, size_t n, int fmt, int c, int nwin, uint32_t nb,
+                                                          const uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor,
+                                                          uint32_t *__restrict__ sorted) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    Fs k = Fs::zero();
+    if (live) { k = load_fe<Fs>(scalars + i); if (fmt == LURK_FMT_MONTGOMERY) k = k.to_canonical(); }
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (c - 1);
+    const uint32_t lane = threadIdx.x & 31;
+    for (int w = 0; w < nwin; w++) {
+        uint32_t raw = window_bits(k.v, w * c, c) + carry;
+        uint32_t neg = raw > half;
+        uint32_t mag = neg ? (1u << c) - raw : raw;
+        carry = neg;
+        uint32_t key = (live && mag) ? (uint32_t)w * nb + (mag - 1) : KEY_NONE;
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
+        uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+        uint32_t base = 0;
+        if (key != KEY_NONE && lane == leader) base = atomicAdd(cursor + key, (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (key != KEY_NONE) {
+            uint32_t rank = __popc(peers & ((1u << lane) - 1));
+            sorted[offsets[key] + base + rank] = (uint32_t)i | (neg << 31);
+        }
+    }
+}
+
+template <class Fb>
+__device__ __forceinline__ Affine<Fb> load_affine(const Affine<Fb> *p) {
+    Affine<Fb> a;
+    a.x = load_fe<Fb>(&p->x);
+    a.y = load_fe<Fb>(&p->y);
+    return a;
+}
+template <class Fb>
+__device__ __forceinline__ XYZZ<Fb> load_xyzz(const XYZZ<Fb> *p) {
+    XYZZ<Fb> a;
+    a.x = load_fe<Fb>(&p->x); a.y = load_fe<Fb>(&p->y); a.zz = load_fe<Fb>(&p->zz); a.zzz = load_fe<Fb>(&p->zzz);
+    return a;
+}
+template <class Fb>
+__device__ __forceinline__ void store_xyzz(XYZZ<Fb> *p, const XYZZ<Fb> &a) {
+    store_fe(&p->x, a.x); store_fe(&p->y, a.y); store_fe(&p->zz, a.zz); store_fe(&p->zzz, a.zzz);
+}
+
+// level 1: fixed-length segments of the sorted list
+template <class Fb>
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__restrict__ offsets, uint32_t nbuckets,
+                                                             const uint32_t *__restrict__ sorted, const Affine<Fb> *__restrict__ bases,
+                                                             XYZZ<Fb> *__restrict__ bucket_acc, uint32_t *__restrict__ pkey,
+                                                             XYZZ<Fb> *__restrict__ ppt, uint32_t seg, uint32_t nthreads) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    const uint32_t total = offsets[nbuckets];
+    const uint64_t start64 = (uint64_t)t * seg;
+    if (start64 >= total) { pkey[t] = KEY_NONE; return; }
+    const uint32_t start = (uint32_t)start64;
+    const uint32_t end = (uint32_t)min((uint64_t)total, start64 + seg);
+    // bucket containing `start`: largest key with offsets[key] <= start
+    uint32_t lo = 0, hi = nbuckets;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= start) lo = mid; else hi = mid;
+    }
+    uint32_t key = lo;
+    uint32_t pos = start;
+    bool first_run = true;
+    uint32_t e_next = sorted[pos];
+    Affine<Fb> p_next = load_affine(bases + (e_next & 0x7fffffffu));
+    while (pos < end) {
+        const uint32_t run_end = min(offsets[key + 1], end);
+        XYZZ<Fb> acc = XYZZ<Fb>::identity();
+        while (pos < run_end) {
+            const uint32_t e = e_next;
+            const Affine<Fb> p = p_next;
+            pos++;
+            if (pos < end) {   // prefetch the next entry while this addition runs
+                e_next = sorted[pos];
+                p_next = load_affine(bases + (e_next & 0x7fffffffu));
+            }
+            acc.add_affine(p, (e >> 31) != 0);
+        }
+        if (first_run) { pkey[t] = key; store_xyzz(ppt + t, acc); first_run = false; }
+        else store_xyzz(bucket_acc + key, acc);   // this run starts exactly at the bucket start: sole initialiser
+        if (pos < end) {
+            key++;
+            while (offsets[key + 1] <= pos) key++;   // skip empty buckets
+        }
+    }
+}
+
+// levels >= 2: the same rule on (key, point) lists; keys are non-decreasing, KEY_NONE only as a tail
+template <class Fb>
+__global__ void __launch_bounds__(128) msm_partial_kernel(const uint32_t *__restrict__ keys_in, const XYZZ<Fb> *__restrict__ pts_in,
+                                                          uint32_t count, XYZZ<Fb> *__restrict__ bucket_acc, uint32_t *__restrict__ keys_out,
+                                                          XYZZ<Fb> *__restrict__ pts_out, uint32_t seg, int last_level) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t s64 = (uint64_t)u * seg;
+    if (s64 >= count) return;
+    const uint32_t s = (uint32_t)s64, e = (uint32_t)min((uint64_t)count, s64 + seg);
+    uint32_t cur = KEY_NONE;
+    bool first_run = true, wrote_out = false;
+    XYZZ<Fb> acc = XYZZ<Fb>::identity();
+    for (uint32_t i = s; i <= e; i++) {
+        const uint32_t k = i < e ? keys_in[i] : KEY_NONE;   // one extra step flushes the last run
+        if (k == cur && k != KEY_NONE) { acc.add(load_xyzz(pts_in + i)); continue; }
+        if (cur != KEY_NONE) {
+            if (first_run && !last_level) { keys_out[u] = cur; store_xyzz(pts_out + u, acc); wrote_out = true; }
+            else { XYZZ<Fb> b = load_xyzz(bucket_acc + cur); b.add(acc); store_xyzz(bucket_acc + cur, b); }
+            first_run = false;
+        }
+        if (k == KEY_NONE) break;
+        cur = k;
+        acc = load_xyzz(pts_in + i);
+    }
+    if (!wrote_out && !last_level) keys_out[u] = KEY_NONE;
+}
+
+// per chunk of `chunk` buckets [b0, b0+chunk) of window w:  sum_b (b+1) B_b = tri + b0 * S
+template <class Fb>
+__global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(const XYZZ<Fb> *__restrict__ bucket_acc, uint32_t nb, uint32_t chunk,
+                                                                uint32_t nchunks_total, XYZZ<Fb> *__restrict__ chunk_out) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nchunks_total) return;
+    const uint32_t per_win = nb / chunk;
+    const uint32_t w = g / per_win, ch = g % per_win;
+    const uint32_t b0 = ch * chunk;
+    const XYZZ<Fb> *B = bucket_acc + (size_t)w * nb + b0;
+    XYZZ<Fb> run = XYZZ<Fb>::identity(), tri = XYZZ<Fb>::identity();
+    for (int b = (int)chunk - 1; b >= 0; b--) {
+        run.add(load_xyzz(B + b));
+        tri.add(run);
+    }
+    if (b0) tri.add(run.mul_u32(b0));
+    store_xyzz(chunk_out + g, tri);
+}
+
+// one CTA per window: sum of its chunk results
+template <class Fb>
+__global__ void __launch_bounds__(256) msm_window_sum_kernel(const XYZZ<Fb> *__restrict__ chunk_in, uint32_t per_win, XYZZ<Fb> *__restrict__ win_out) {
+    __shared__ XYZZ<Fb> sm[256];
+    const uint32_t w = blockIdx.x, tid = threadIdx.x;
+    XYZZ<Fb> acc = XYZZ<Fb>::identity();
+    for (uint32_t i = tid; i < per_win; i += blockDim.x) acc.add(load_xyzz(chunk_in + (size_t)w * per_win + i));
+    sm[tid] = acc;
+    __syncthreads();
+    for (uint32_t stride = blockDim.x / 2; stride > 0; stride >>= 1) {
+        if (tid < stride) { XYZZ<Fb> a = sm[tid]; a.add(sm[tid + stride]); sm[tid] = a; }
+        __syncthreads();
+    }
+    if (tid == 0) store_xyzz(win_out + w, sm[0]);
+}
+
+// affine bases: canonical -> Montgomery in place
+template <class Fb>
+__global__ void __launch_bounds__(256) msm_bases_to_mont_kernel(Fb *coords, size_t count) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        store_fe(coords + i, Fb::from_canonical(load_fe<Fb>(coords + i)));
+}
+
+// ----------------------------------------------------------------------------- context
+struct MsmScratch {
+    DevBuf counts, offsets, sorted, buckets, pkey[2], ppt[2], chunks, wins, scalars;
+    void *h_wins = nullptr;   // pinned
+    ~MsmScratch() { if (h_wins) cudaFreeHost(h_wins); }
+};
+
+}  // namespace lurk
+
+using namespace lurk;
+
+struct lurk_msm_ctx {
+    int curve_id = 0;
+    int device = 0;
+    size_t n = 0;
+    void *d_bases = nullptr;
+    bool owns_bases = false;
+    std::mutex mu;
+    MsmScratch scratch;
+};
+
+namespace lurk {
+
+template <class Fb>
+static void point_to_bytes(const XYZZ<Fb> &p, int fmt, uint8_t out[96]) {
+    memset(out, 0, 96);
+    if (p.is_identity()) return;
+    Affine<Fb> a = p.to_affine();
+    Fb one = Fb::one();
+    if (fmt == LURK_FMT_CANONICAL) { a.x = a.x.to_canonical(); a.y = a.y.to_canonical(); one = one.to_canonical(); }
+    memcpy(out, a.x.v, 32); memcpy(out + 32, a.y.v, 32); memcpy(out + 64, one.v, 32);
+}
+
+template <class C>
+static int msm_run(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, uint8_t out[96], cudaStream_t s) {
+    using Fb = typename C::Base;
+    using Fs = typename C::Scalar;
+    using Pt = XYZZ<Fb>;
+    if (n == 0) { memset(out, 0, 96); return LURK_OK; }
+    MsmPlan P = make_plan(n, Fs::Params::NBITS);
+    MsmScratch &S = ctx->scratch;
+    {
+        // scratch grows monotonically; a context is normally run at one size (the circuit's witness length)
+        auto ensure = [](DevBuf &b, size_t bytes) { return b.bytes >= bytes ? LURK_OK : b.alloc(bytes); };
+        LURK_TRY(ensure(S.counts, ((size_t)P.total_buckets + 1) * 2 * sizeof(uint32_t)));   // counts | cursor
+        LURK_TRY(ensure(S.offsets, ((size_t)P.total_buckets + 1) * sizeof(uint32_t)));
+        LURK_TRY(ensure(S.sorted, n * (size_t)P.nwin * sizeof(uint32_t)));
+        LURK_TRY(ensure(S.buckets, (size_t)P.total_buckets * sizeof(Pt)));
+        LURK_TRY(ensure(S.pkey[0], (size_t)P.t1 * sizeof(uint32_t)));
+        LURK_TRY(ensure(S.ppt[0], (size_t)P.t1 * sizeof(Pt)));
+        size_t t2 = ((size_t)P.t1 + 31) / 32;
+        LURK_TRY(ensure(S.pkey[1], t2 * sizeof(uint32_t)));
+        LURK_TRY(ensure(S.ppt[1], t2 * sizeof(Pt)));
+        LURK_TRY(ensure(S.chunks, (size_t)(P.total_buckets / P.chunk) * sizeof(Pt)));
+        LURK_TRY(ensure(S.wins, 64 * sizeof(Pt)));
+        if (!S.h_wins) LURK_CUDA_TRY(cudaMallocHost(&S.h_wins, 64 * sizeof(Pt)));
+    }
+    const uint32_t TB = P.total_buckets;
+    uint32_t *counts = S.counts.as<uint32_t>();
+    uint32_t *cursor = counts + (TB + 1);
+    uint32_t *offsets = S.offsets.as<uint32_t>();
+    uint32_t *sorted = S.sorted.as<uint32_t>();
+    Pt *buckets = S.buckets.as<Pt>();
+
+    LURK_CUDA_TRY(cudaMemsetAsync(counts, 0, ((size_t)TB + 1) * 2 * sizeof(uint32_t), s));
+    LURK_CUDA_TRY(cudaMemsetAsync(buckets, 0, (size_t)TB * sizeof(Pt), s));   // all-zero = identity
+    const unsigned gs = (unsigned)((n + 255) / 256);
+    msm_count_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, P.nb, counts);
+    msm_scan_kernel<<<1, 1024, 0, s>>>(counts, TB, offsets);
+    msm_scatter_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, P.nb, offsets, cursor, sorted);
+    msm_accumulate_kernel<Fb><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, (const Affine<Fb> *)ctx->d_bases, buckets,
+                                                                S.pkey[0].as<uint32_t>(), S.ppt[0].as<Pt>(), P.seg, P.t1);
+    // shrinking passes over the partial list
+    uint32_t count = P.t1;
+    int cur = 0;
+    for (;;) {
+        const uint32_t seg2 = 32;
+        const uint32_t threads = (count + seg2 - 1) / seg2;
+        const int last = threads == 1;
+        msm_partial_kernel<Fb><<<(threads + 127) / 128, 128, 0, s>>>(S.pkey[cur].as<uint32_t>(), S.ppt[cur].as<Pt>(), count, buckets,
+                                                                    S.pkey[cur ^ 1].as<uint32_t>(), S.ppt[cur ^ 1].as<Pt>(), seg2, last);
+        if (last) break;
+        count = threads;
+        cur ^= 1;
+    }
+    const uint32_t nchunks = TB / P.chunk;
+    msm_bucket_reduce_kernel<Fb><<<(nchunks + 127) / 128, 128, 0, s>>>(buckets, P.nb, P.chunk, nchunks, S.chunks.as<Pt>());
+    msm_window_sum_kernel<Fb><<<P.nwin, 256, 0, s>>>(S.chunks.as<Pt>(), P.nb / P.chunk, S.wins.as<Pt>());
+    LURK_CUDA_TRY(cudaGetLastError());
+    LURK_CUDA_TRY(cudaMemcpyAsync(S.h_wins, S.wins.p, (size_t)P.nwin * sizeof(Pt), cudaMemcpyDeviceToHost, s));
+    LURK_CUDA_TRY(cudaStreamSynchronize(s));
+    // Horner over the windows on the host
+    const Pt *w = reinterpret_cast<const Pt *>(S.h_wins);
+    Pt acc = Pt::identity();
+    for (int i = P.nwin - 1; i >= 0; i--) {
+        for (int d = 0; d < P.c; d++) acc = acc.dbl();
+        acc.add(w[i]);
+    }
+    point_to_bytes(acc, fmt, out);
+    return LURK_OK;
+}
+
+template <class C>
+static int ctx_upload(lurk_msm_ctx *ctx, const uint8_t *bases, size_t n, int fmt) {
+    using Fb = typename C::Base;
+    LURK_CUDA_TRY(cudaMalloc(&ctx->d_bases, n * 64));
+    ctx->owns_bases = true;
+    LURK_CUDA_TRY(cudaMemcpy(ctx->d_bases, bases, n * 64, cudaMemcpyHostToDevice));
+    int bad = 0;
+    LURK_TRY(check_reduced_dev<Fb>(ctx->d_bases, n * 2, 0, &bad));
+    if (bad) { set_error("%d base coordinate(s) are not reduced below the field modulus", bad); return LURK_ERR_RANGE; }
+    if (fmt == LURK_FMT_CANONICAL) {
+        msm_bases_to_mont_kernel<Fb><<<sm_count() * 8, 256>>>((Fb *)ctx->d_bases, n * 2);
+        LURK_CUDA_TRY(cudaGetLastError());
+        LURK_CUDA_TRY(cudaDeviceSynchronize());
+    }
+    return LURK_OK;
+}
+
+}  // namespace lurk
+
+extern "C" {
+
+int lurk_msm_ctx_create_dev(int curve_id, const void *d_bases_mont, size_t n, lurk_msm_ctx **out) {
+    if (!out) { set_error("null out"); return LURK_ERR_ARG; }
+    *out = nullptr;
+    if (curve_id < 0 || curve_id > 3) { set_error("unknown curve id %d", curve_id); return LURK_ERR_ARG; }
+    if (n >= ((size_t)1 << 31)) { set_error("commitment key too large"); return LURK_ERR_ARG; }
+    LURK_TRY(require_gpu());
+    lurk_msm_ctx *ctx = new lurk_msm_ctx();
+    ctx->curve_id = curve_id;
+    ctx->n = n;
+    ctx->d_bases = const_cast<void *>(d_bases_mont);
+    cudaGetDevice(&ctx->device);
+    *out = ctx;
+    return LURK_OK;
+}
+
+int lurk_msm_ctx_create(int curve_id, const uint8_t *bases_affine, size_t n, int fmt, lurk_msm_ctx **out) {
+    if (fmt != LURK_FMT_CANONICAL && fmt != LURK_FMT_MONTGOMERY) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
+    if (n && !bases_affine) { set_error("null bases"); return LURK_ERR_ARG; }
+    LURK_TRY(lurk_msm_ctx_create_dev(curve_id, nullptr, n, out));
+    if (n == 0) return LURK_OK;
+    int rc = dispatch_curve(curve_id, [&](auto c) { return ctx_upload<decltype(c)>(*out, bases_affine, n, fmt); });
+    if (rc != LURK_OK) { lurk_msm_ctx_destroy(*out); *out = nullptr; }
+    return rc;
+}
+
+void lurk_msm_ctx_destroy(lurk_msm_ctx *ctx) {
+    if (!ctx) return;
+    if (ctx->owns_bases && ctx->d_bases) cudaFree(ctx->d_bases);
+    delete ctx;
+}
+
+int lurk_msm_ctx_run_dev(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, uint8_t out_xyz[96], void *stream) {
+    if (!ctx || !out_xyz) { set_error("null argument"); return LURK_ERR_ARG; }
+    if (fmt != LURK_FMT_CANONICAL && fmt != LURK_FMT_MONTGOMERY) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
+    if (n > ctx->n) { set_error("%zu scalars for a commitment key of %zu bases", n, ctx->n); return LURK_ERR_ARG; }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    return dispatch_curve(ctx->curve_id, [&](auto c) { return msm_run<decltype(c)>(ctx, d_scalars, n, fmt, out_xyz, (cudaStream_t)stream); });
+}
+
+int lurk_msm_ctx_run(lurk_msm_ctx *ctx, const uint8_t *scalars, size_t n, int fmt, uint8_t out_xyz[96]) {
+    if (!ctx || !out_xyz || (n && !scalars)) { set_error("null argument"); return LURK_ERR_ARG; }
+    if (n > ctx->n) { set_error("%zu scalars for a commitment key of %zu bases", n, ctx->n); return LURK_ERR_ARG; }
+    if (n == 0) { memset(out_xyz, 0, 96); return LURK_OK; }
+    if (fmt != LURK_FMT_CANONICAL && fmt != LURK_FMT_MONTGOMERY) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (ctx->scratch.scalars.bytes < n * 32) LURK_TRY(ctx->scratch.scalars.alloc(n * 32));
+    LURK_CUDA_TRY(cudaMemcpy(ctx->scratch.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice));
+    int bad = 0;
+    LURK_TRY(dispatch_curve(ctx->curve_id, [&](auto c) {
+        using Fs = typename decltype(c)::Scalar;
+        return check_reduced_dev<Fs>(ctx->scratch.scalars.p, n, 0, &bad);
+    }));
+    if (bad) { set_error("%d scalar(s) are not reduced below the group order", bad); return LURK_ERR_RANGE; }
+    return dispatch_curve(ctx->curve_id, [&](auto c) { return msm_run<decltype(c)>(ctx, ctx->scratch.scalars.p, n, fmt, out_xyz, nullptr); });
+}
+
+int lurk_msm(int curve_id, const uint8_t *bases_affine, const uint8_t *scalars, size_t n, int fmt, uint8_t out_xyz[96]) {
+    lurk_msm_ctx *ctx = nullptr;
+    LURK_TRY(lurk_msm_ctx_create(curve_id, bases_affine, n, fmt, &ctx));
+    int rc = lurk_msm_ctx_run(ctx, scalars, n, fmt, out_xyz);
+    lurk_msm_ctx_destroy(ctx);
+    return rc;
+}
+
+int lurk_synthetic_bases(int curve_id, uint64_t start, size_t n, int fmt, uint8_t *bases_out) {
+    if (!bases_out && n) { set_error("null output"); return LURK_ERR_ARG; }
+    if (fmt != LURK_FMT_CANONICAL && fmt != LURK_FMT_MONTGOMERY) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
+    return dispatch_curve(curve_id, [&](auto c) {
+        using Cv = decltype(c);
+        using Fb = typename Cv::Base;
+        const Affine<Fb> g = curve_generator<Cv>();
+        const size_t BATCH = 1 << 12;
+        unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        const size_t nbatches = (n + BATCH - 1) / BATCH;
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            std::vector<XYZZ<Fb>> pts(BATCH);
+            std::vector<Fb> pref(BATCH);
+            for (;;) {
+                size_t b = next.fetch_add(1);
+                if (b >= nbatches) break;
+                size_t lo = b * BATCH, m = std::min(BATCH, n - lo);
+                // [start + lo + 1] G by double-and-add, then a running sum
+                uint64_t k = start + lo + 1;
+                XYZZ<Fb> acc = XYZZ<Fb>::identity();
+                for (int bit = 63; bit >= 0; bit--) { acc = acc.dbl(); if ((k >> bit) & 1) acc.add_affine(g); }
+                for (size_t i = 0; i < m; i++) { pts[i] = acc; acc.add_affine(g); }
+                // one inversion per batch (Montgomery's trick on the ZZZ coordinates)
+                Fb run = Fb::one();
+                for (size_t i = 0; i < m; i++) { pref[i] = run; run = run * pts[i].zzz; }
+                Fb inv = run.inv();
+                for (size_t i = m; i-- > 0;) {
+                    Fb zi = inv * pref[i];            // 1 / ZZZ_i
+                    inv = inv * pts[i].zzz;
+                    Fb zz_inv = (zi * pts[i].zz).sqr();
+                    Fb x = pts[i].x * zz_inv, y = pts[i].y * zi;
+                    if (fmt == LURK_FMT_CANONICAL) { x = x.to_canonical(); y = y.to_canonical(); }
+                    memcpy(bases_out + 64 * (lo + i), x.v, 32);
+                    memcpy(bases_out + 64 * (lo + i) + 32, y.v, 32);
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(worker);
+        worker();
+        for (auto &t : pool) t.join();
+        return LURK_OK;
+    });
+}
+
+int lurk_point_sum(int curve_id, const uint8_t *points_xyz, size_t count, int fmt, uint8_t out_xyz[96]) {
+    if (!out_xyz || (count && !points_xyz)) { set_error("null argument"); return LURK_ERR_ARG; }
+    if (fmt != LURK_FMT_CANONICAL && fmt != LURK_FMT_MONTGOMERY) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
+    return dispatch_curve(curve_id, [&](auto c) {
+        using Fb = typename decltype(c)::Base;
+        XYZZ<Fb> acc = XYZZ<Fb>::identity();
+        for (size_t i = 0; i < count; i++) {
+            const uint8_t *p = points_xyz + 96 * i;
+            Fb x, y, z;
+            memcpy(x.v, p, 32); memcpy(y.v, p + 32, 32); memcpy(z.v, p + 64, 32);
+            if (!x.is_reduced() || !y.is_reduced()) { set_error("point %zu is not reduced", i); return LURK_ERR_RANGE; }
+            if (z.is_zero()) continue;
+            Affine<Fb> a;
+            a.x = fmt == LURK_FMT_CANONICAL ? Fb::from_canonical(x) : x;
+            a.y = fmt == LURK_FMT_CANONICAL ? Fb::from_canonical(y) : y;
+            acc.add_affine(a);
+        }
+        point_to_bytes(acc, fmt, out_xyz);
+        return LURK_OK;
+    });
+}
+
+}  // extern "C"

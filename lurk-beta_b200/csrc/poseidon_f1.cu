@@ -1,0 +1,3 @@
+// Poseidon kernels instantiated for Fe<Bn254Fq> (one translation unit per field keeps the build parallel).
+#include "poseidon_kernel.cuh"
+namespace lurk { LURK_POSEIDON_INSTANTIATE(Fe<Bn254Fq>) }

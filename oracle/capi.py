@@ -104,7 +104,8 @@ def bitdecomp_witness_batch(field_id, vals, nthreads=1):
     return out
 
 
-DAG_NODE = np.dtype([("kind", "u1"), ("pad", "u1"), ("tag", "<u2", (4,)), ("child", "<u4", (4,))])
+DAG_NODE = np.dtype([("kind", "u1"), ("pad", "u1"), ("tag", "<u2", (4,)), ("child", "<u4", (4,))], align=True)   # C layout, 28 bytes
+assert DAG_NODE.itemsize == 28
 
 
 def dag_hash(field_id, nodes, atoms):

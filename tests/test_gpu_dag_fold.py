@@ -1,0 +1,151 @@
+"""GPU parity for S2 (store hydration), S5 (fold helpers) and K6 (NTT) against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import GOLDEN, TAG_CHAR, TAG_NIL, TAG_STR, TAG_SYM, ints, pack, random_elements
+
+pytestmark = pytest.mark.gpu
+
+
+def test_store_symbol_hashing_golden(L):
+    # (commit nil): nil = symbol .lurk.nil; strings are H4 chains of chars, symbols H4 chains of strings
+    # (src/lem/store.rs:1368-1412); golden src/lem/tests/eval_tests.rs:1955
+    s = L.StoreCore(L.FIELD_BN254_FR)
+    zero_str = s.intern_atom(TAG_STR, 0)
+    zero_sym = s.intern_atom(TAG_SYM, 0)
+
+    def intern_str(text):
+        ptr = zero_str
+        for ch in reversed(text):
+            ptr = s.intern_tuple2([s.intern_atom(TAG_CHAR, ord(ch)), ptr], TAG_STR)
+        return ptr
+
+    sym = zero_sym
+    for name in ["lurk", "nil"]:
+        sym = s.intern_tuple2([intern_str(name), sym], TAG_SYM)
+    nil = (TAG_NIL, sym[1])
+    assert len(s.dehydrated) == 9          # 7 string conses + 2 symbol conses, nothing hashed yet
+    assert s.hide(0, nil) == GOLDEN["G8"]
+    assert not s.dehydrated or all(v in s.z_cache for v in s.dehydrated)
+    assert s.open(GOLDEN["G8"]) == (0, nil)
+
+
+def test_store_basic_hashing_matches_flat_hashes(L):
+    # mirror of test_basic_hashing (src/lem/store.rs:1305-1338)
+    s = L.StoreCore(L.FIELD_BN254_FR)
+    z = s.intern_atom(0, 0)
+    t2 = s.intern_tuple2([z, z], 1)
+    t3 = s.intern_tuple3([z, z, z], 1)
+    t4 = s.intern_tuple4([z, z, z, z], 1)
+    s.hydrate_z_cache()
+    pc = s.hasher
+    assert s.hash_ptr(t2)[1] == pc.hash4([0] * 4)
+    assert s.hash_ptr(t3)[1] == pc.hash6([0] * 6)
+    assert s.hash_ptr(t4)[1] == pc.hash8([0] * 8)
+    env = s.intern_compact([z, t2, t3], 1)
+    assert s.hash_ptr(env)[1] == pc.hash_compact(0, 1, s.hash_ptr_val(t2[1]), s.hash_ptr_val(t3[1]))
+
+
+@pytest.mark.parametrize("field", [0, 2])
+def test_random_dag_parity(L, oracle, field):
+    rng = np.random.default_rng(12)
+    n_atoms, n = 50, 3000
+    atoms = random_elements(field, n_atoms, seed=3)
+    nodes = np.zeros(n, dtype=oracle.DAG_NODE)
+    kinds = [2, 3, 4, 5, 6]
+    for i in range(n):
+        k = kinds[rng.integers(0, 5)]
+        nodes[i]["kind"] = k
+        nodes[i]["tag"] = rng.integers(0, 0x3014, size=4)
+        # mix of shallow and deep references; a long dependent chain every 7th node
+        hi = n_atoms + i
+        ch = rng.integers(0, hi, size=4)
+        if i and i % 7 == 0:
+            ch[0] = hi - 1
+        nodes[i]["child"] = ch
+    out = np.zeros(n * 32, dtype=np.uint8)
+    L._capi.check(L._capi.lib().lurk_dag_hash(field, L._capi.np_ptr(nodes), n, L._capi.np_ptr(atoms), n_atoms, L._capi.np_ptr(out)))
+    assert np.array_equal(out, oracle.dag_hash(field, nodes, atoms))
+    # ordering violation is reported, not executed
+    bad = nodes.copy()
+    bad[0]["child"][0] = n_atoms + 5
+    rc = L._capi.lib().lurk_dag_hash(field, L._capi.np_ptr(bad), n, L._capi.np_ptr(atoms), n_atoms, L._capi.np_ptr(out))
+    assert rc == L._capi.ERR_ORDER
+
+
+def dev(arr):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+
+
+def mont(spec, field, buf):
+    p = spec.FIELD_MODULUS[field]
+    return pack([x * (1 << 256) % p for x in ints(buf)])
+
+
+def unmont(spec, field, buf):
+    p = spec.FIELD_MODULUS[field]
+    rinv = pow(1 << 256, -1, p)
+    return [x * rinv % p for x in ints(buf)]
+
+
+@pytest.mark.parametrize("field", [0, 1, 2, 3])
+def test_fold_helpers_parity(L, oracle, spec, field):
+    import torch
+    lib = L._capi.lib()
+    n = 5000
+    a, b = random_elements(field, n, 1, "witness"), random_elements(field, n, 2)
+    r = random_elements(field, 1, 3)
+    da, db = dev(mont(spec, field, a)), dev(mont(spec, field, b))
+    out = torch.empty_like(da)
+    L._capi.check(lib.lurk_axpy_dev(field, da.data_ptr(), db.data_ptr(), L._capi.np_ptr(mont(spec, field, r)), n, out.data_ptr(), None))
+    assert unmont(spec, field, out.cpu().numpy()) == ints(oracle.axpy(field, a, b, r))
+    # conversion kernel round trip
+    canon = torch.empty_like(da)
+    L._capi.check(lib.lurk_convert_dev(field, da.data_ptr(), n, L.FMT_CANONICAL, canon.data_ptr(), None))
+    assert np.array_equal(canon.cpu().numpy(), a)
+    # CSR SpMV with R1CS-like rows (0..6 non-zeros, small coefficients and -1)
+    rng = np.random.default_rng(5)
+    rows = 3000
+    nnz_per = rng.integers(0, 7, size=rows)
+    row_ptr = np.concatenate([[0], np.cumsum(nnz_per)]).astype(np.uint64)
+    col = rng.integers(0, n, size=int(row_ptr[-1])).astype(np.uint32)
+    p = spec.FIELD_MODULUS[field]
+    val = pack([[1, p - 1, 2, 5, 7, (1 << 64) + 3][k] for k in rng.integers(0, 6, size=col.size)])
+    y = torch.empty(rows * 32, dtype=torch.uint8, device="cuda")
+    L._capi.check(lib.lurk_spmv_csr_dev(field, dev(row_ptr).data_ptr(), dev(col).data_ptr(), dev(mont(spec, field, val)).data_ptr(),
+                                        rows, da.data_ptr(), y.data_ptr(), None))
+    assert unmont(spec, field, y.cpu().numpy()) == ints(oracle.spmv(field, row_ptr, col, val, a))
+    # cross term
+    v = [random_elements(field, 1000, 20 + k) for k in range(6)]
+    u1, u2 = random_elements(field, 1, 30), pack([1])
+    dv = [dev(mont(spec, field, x)) for x in v]
+    t = torch.empty_like(dv[0])
+    L._capi.check(lib.lurk_cross_term_dev(field, *[x.data_ptr() for x in dv], L._capi.np_ptr(mont(spec, field, u1)),
+                                          L._capi.np_ptr(mont(spec, field, u2)), 1000, t.data_ptr(), None))
+    assert unmont(spec, field, t.cpu().numpy()) == ints(oracle.cross_term(field, *v, u1, u2))
+
+
+@pytest.mark.parametrize("field", [0, 2, 3])
+@pytest.mark.parametrize("log_n", [1, 4, 10, 13, 16])
+def test_ntt_parity(L, oracle, spec, field, log_n):
+    import torch
+    lib = L._capi.lib()
+    n = 1 << log_n
+    a = random_elements(field, n, seed=log_n)
+    d = dev(mont(spec, field, a))
+    L._capi.check(lib.lurk_ntt_dev(field, d.data_ptr(), log_n, 0, None))
+    got = unmont(spec, field, d.cpu().numpy())
+    assert got == ints(oracle.ntt(field, a, nthreads=8))
+    if log_n <= 4:
+        assert got == spec.ntt_naive(field, ints(a))
+    L._capi.check(lib.lurk_ntt_dev(field, d.data_ptr(), log_n, 1, None))     # inverse round trip
+    assert unmont(spec, field, d.cpu().numpy()) == ints(a)
+
+
+def test_ntt_rejects_unsupported_size(L):
+    import torch
+    d = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    assert L._capi.lib().lurk_ntt_dev(L.FIELD_BN254_FQ, d.data_ptr(), 2, 0, None) == L._capi.ERR_ARG   # 2-adicity 1

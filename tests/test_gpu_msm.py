@@ -1,0 +1,99 @@
+"""GPU parity for S4: Pippenger MSM through the C ABI against the oracle (plain-C Jacobian Pippenger and naive
+double-and-add), compared as canonical affine points -- the group law is canonical, so any correct MSM is bit-exact
+after normalisation."""
+import numpy as np
+import pytest
+
+from util import ints, pack, random_elements
+
+pytestmark = pytest.mark.gpu
+CURVES = [0, 1, 2, 3]
+
+
+def scalars_for(spec, curve, n, seed, shape):
+    return random_elements(spec.CURVES[curve]["scalar"], n, seed=seed, shape=shape)
+
+
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("n", [1, 2, 33, 1000])
+def test_msm_parity_small(L, oracle, spec, curve, n):
+    bases = oracle.gen_bases(curve, n)
+    sc = scalars_for(spec, curve, n, seed=n + curve, shape="uniform")
+    got = L.CommitmentKey(curve, bases).commit(sc)
+    want = oracle.msm(curve, bases, sc, nthreads=4, naive=(n <= 33))
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("shape", ["uniform", "witness"])
+def test_msm_parity_2_16(L, oracle, spec, curve, shape):
+    n = 1 << 16
+    bases = oracle.gen_bases(curve, n)
+    sc = scalars_for(spec, curve, n, seed=11 + curve, shape=shape)
+    got = L.CommitmentKey(curve, bases).commit(sc)
+    want = oracle.msm(curve, bases, sc, nthreads=8)
+    assert np.array_equal(got, want)
+
+
+def test_msm_edge_scalars_and_identity_bases(L, oracle, spec):
+    curve, n = 2, 600
+    q = spec.FIELD_MODULUS[spec.CURVES[curve]["scalar"]]
+    bases = oracle.gen_bases(curve, n)
+    bases[64 * 5:64 * 6] = 0                      # identity base (0, 0) is skipped
+    bases[64 * 9:64 * 10] = bases[64 * 8:64 * 9]  # duplicate point: exercises the doubling branch
+    ck = L.CommitmentKey(curve, bases)
+    for vals in ([0] * n, [1] * n, [q - 1] * n, [2] * n, [q - 1, 1] * (n // 2), [(1 << 254) - 3] * n):
+        sc = pack(vals)
+        assert np.array_equal(ck.commit(sc), oracle.msm(curve, bases, sc, nthreads=4)), vals[:2]
+    # prefix of the key (|W| < |ck|) and empty input
+    sc = scalars_for(spec, curve, 100, seed=5, shape="witness")
+    assert np.array_equal(ck.commit(sc), oracle.msm(curve, bases[:6400], sc))
+    assert not ck.commit(np.zeros(0, dtype=np.uint8)).any()
+    # P + (-P) = identity
+    two = pack([5, q - 5])
+    same = np.concatenate([bases[:64], bases[:64]])
+    assert not L.CommitmentKey(curve, same).commit(two).any()
+
+
+def test_msm_errors(L, oracle, spec):
+    curve = 0
+    bases = oracle.gen_bases(curve, 4)
+    ck = L.CommitmentKey(curve, bases)
+    with pytest.raises(L.LurkError):
+        ck.commit(pack([1] * 5))                  # more scalars than bases
+    with pytest.raises(L.LurkError) as e:
+        ck.commit(pack([spec.FIELD_MODULUS[spec.CURVES[curve]["scalar"]]] * 2))
+    assert e.value.code == L._capi.ERR_RANGE
+
+
+def test_msm_montgomery_format(L, oracle, spec):
+    curve, n = 0, 500
+    C = spec.CURVES[curve]
+    pb, q = spec.FIELD_MODULUS[C["base"]], spec.FIELD_MODULUS[C["scalar"]]
+    bases = oracle.gen_bases(curve, n)
+    sc = scalars_for(spec, curve, n, seed=2, shape="uniform")
+    R = 1 << 256
+    bm = pack([x * R % pb for x in ints(bases)])
+    sm = pack([x * R % q for x in ints(sc)])
+    got = L.CommitmentKey(curve, bm, fmt=L.FMT_MONTGOMERY).commit(sm, fmt=L.FMT_MONTGOMERY)
+    want = oracle.msm(curve, bases, sc, nthreads=4)
+    rinv = pow(R, -1, pb)
+    assert [v * rinv % pb for v in ints(got)] == ints(want)
+
+
+def test_msm_linearity_2_20(L, oracle, spec):
+    """size-independent property at a size the oracle cannot check directly quickly: commit is linear,
+    commit(a) + commit(b) == commit(a + b), and agrees with the oracle on a 2^14 prefix."""
+    curve, n = 0, 1 << 20
+    q = spec.FIELD_MODULUS[spec.CURVES[curve]["scalar"]]
+    bases = oracle.gen_bases(curve, n)
+    ck = L.CommitmentKey(curve, bases)
+    a = scalars_for(spec, curve, n, seed=21, shape="witness")
+    b = scalars_for(spec, curve, n, seed=22, shape="uniform")
+    a64 = a.reshape(-1, 32).view("<u8").astype(object)
+    # a + b mod q with python ints on a strided subset would be slow for 2^20; use the oracle's axpy (r = 1)
+    ab = oracle.axpy(spec.CURVES[curve]["scalar"], a, b, pack([1]), nthreads=8)
+    ca, cb, cab = ck.commit(a), ck.commit(b), ck.commit(ab)
+    assert np.array_equal(L.point_sum(curve, np.concatenate([ca, cb])), cab)
+    m = 1 << 14
+    assert np.array_equal(ck.commit(a[:32 * m]), oracle.msm(curve, bases[:64 * m], a[:32 * m], nthreads=8))

@@ -1,0 +1,126 @@
+"""GPU parity for S1/S3: CUDA Poseidon digests, slot witnesses and bit-decomposition witnesses, through the C ABI,
+bit-exact against the oracle.  Model: the reference's sequential-vs-parallel witness equivalence test
+(src/lem/multiframe.rs:1019-1125)."""
+import numpy as np
+import pytest
+
+from util import GOLDEN, TAG_NUM, ints, pack, random_elements
+
+pytestmark = pytest.mark.gpu
+FIELDS = [0, 1, 2, 3]
+ARITIES = [3, 4, 6, 8]
+
+
+def test_golden_digests_through_c_abi(L):
+    pc = L.PoseidonCache(L.FIELD_BN254_FR)
+    d = pc.hash8([0] * 8)
+    assert d == GOLDEN["G1"]
+    seq = [d]
+    for _ in range(84):
+        seq.append(pc.hash8([seq[-1]] * 8))
+    assert (seq[1], seq[2], seq[3], seq[84]) == (GOLDEN["G2"], GOLDEN["G3"], GOLDEN["G4"], GOLDEN["G5"])
+    assert pc.hash3([0, TAG_NUM, 0]) == GOLDEN["G6"]
+    assert pc.hash3([0, TAG_NUM, 123]) == GOLDEN["G7"]
+    assert pc.compute_hash([0, TAG_NUM, 123]) == GOLDEN["G7"]
+    with pytest.raises(ValueError):
+        pc.compute_hash([1, 2])            # unsupported arity (reference panics, src/hash.rs:26)
+
+
+@pytest.mark.parametrize("field", FIELDS)
+@pytest.mark.parametrize("arity", ARITIES)
+@pytest.mark.parametrize("shape", ["uniform", "lem"])
+def test_digest_parity_small_batch(L, oracle, spec, field, arity, shape):
+    n = 257                                    # ragged: not a multiple of the warp / CTA size
+    pre = random_elements(field, n * arity, seed=1000 * field + 10 * arity + len(shape), shape=shape)
+    p = spec.FIELD_MODULUS[field]
+    pre[:arity * 32] = 0                                          # all-zero preimage (dummy slot)
+    pre[arity * 32:2 * arity * 32] = pack([p - 1] * arity)        # maximum elements
+    got = L.PoseidonCache(field).hash_batch_bytes(arity, pre)
+    want = oracle.poseidon_hash_batch(field, arity, pre, mode=1, nthreads=8)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("field,arity", [(0, 8), (0, 4), (2, 8), (2, 4), (1, 3), (3, 6)])
+def test_digest_parity_throughput_path(L, oracle, field, arity):
+    # large enough for the persistent one-CTA-per-SM launch shape; oracle on 8 threads takes seconds
+    n = 148 * 512 + 77
+    pre = random_elements(field, n * arity, seed=55 + field + arity)
+    got = L.PoseidonCache(field).hash_batch_bytes(arity, pre)
+    want = oracle.poseidon_hash_batch(field, arity, pre, mode=1, nthreads=8)
+    assert np.array_equal(got, want)
+
+
+def test_digest_montgomery_entry_point(L, oracle, spec):
+    import ctypes as C
+    field, arity, n = 0, 4, 100
+    p = spec.FIELD_MODULUS[field]
+    pre = random_elements(field, n * arity, seed=4)
+    mont = pack([x * (1 << 256) % p for x in ints(pre)])
+    out = np.zeros(n * 32, dtype=np.uint8)
+    L._capi.check(L._capi.lib().lurk_poseidon_hash_batch_mont(field, arity, L._capi.np_ptr(mont), n, L._capi.np_ptr(out)))
+    want = ints(oracle.poseidon_hash_batch(field, arity, pre))
+    assert [x * pow(1 << 256, -1, p) % p for x in ints(out)] == want
+
+
+def test_empty_and_errors(L, spec):
+    pc = L.PoseidonCache(0)
+    assert pc.hash_batch_bytes(8, np.zeros(0, dtype=np.uint8)).size == 0
+    bad = pack([spec.FIELD_MODULUS[0]] + [0] * 7)       # not reduced: from_repr would fail (src/field.rs:76-81)
+    with pytest.raises(L.LurkError) as e:
+        pc.hash_batch_bytes(8, bad)
+    assert e.value.code == L._capi.ERR_RANGE
+    with pytest.raises(ValueError):
+        pc.hash_batch_bytes(5, np.zeros(5 * 32, dtype=np.uint8))
+
+
+@pytest.mark.parametrize("field", FIELDS)
+@pytest.mark.parametrize("arity", ARITIES)
+def test_slot_witness_parity(L, oracle, field, arity):
+    st = {3: L.SlotType.Commitment, 4: L.SlotType.Hash4, 6: L.SlotType.Hash6, 8: L.SlotType.Hash8}[arity]
+    n = 67
+    pre = random_elements(field, n * arity, seed=31 * field + arity, shape="lem")
+    pre[:arity * 32] = 0
+    got = L.slot_witness_batch_bytes(field, st, pre)
+    want = oracle.poseidon_witness_batch(field, arity, pre, nthreads=8)
+    assert L.compute_witness_size(st, field) == oracle.witness_block(field, arity)
+    assert np.array_equal(got, want)
+
+
+def test_slot_witness_montgomery_format(L, oracle, spec):
+    field, arity, n = 0, 4, 9
+    p = spec.FIELD_MODULUS[field]
+    pre = random_elements(field, n * arity, seed=77)
+    mont = pack([x * (1 << 256) % p for x in ints(pre)])
+    got = L.slot_witness_batch_bytes(field, L.SlotType.Hash4, mont, fmt=L.FMT_MONTGOMERY)
+    want = ints(oracle.poseidon_witness_batch(field, arity, pre))
+    assert [x * pow(1 << 256, -1, p) % p for x in ints(got)] == want
+
+
+@pytest.mark.parametrize("field", FIELDS)
+def test_bitdecomp_witness_parity(L, oracle, spec, field):
+    p = spec.FIELD_MODULUS[field]
+    vals = pack([0, 1, p - 1, p >> 1, (1 << 64) - 1])
+    vals = np.concatenate([vals, random_elements(field, 200, seed=8), random_elements(field, 60, seed=9, shape="witness")])
+    got = L.slot_witness_batch_bytes(field, L.SlotType.BitDecomp, vals)
+    want = oracle.bitdecomp_witness_batch(field, vals, nthreads=4)
+    assert L.compute_witness_size(L.SlotType.BitDecomp, field) == oracle.bitdecomp_size(field)
+    assert np.array_equal(got, want)
+
+
+def test_generate_slots_witnesses_frame_layout(L, oracle):
+    # one frame of the universal step circuit: 14 hash4, 0 hash6, 6 hash8, 1 commitment, 3 bit-decomp
+    # (src/lem/eval.rs:1960-1964), mostly dummy slots
+    ST = L.SlotType
+    rnd = lambda k, seed: ints(random_elements(0, k, seed=seed, shape="lem"))
+    slots = [(ST.Hash4, rnd(4, 1))] + [(ST.Hash4, None)] * 12 + [(ST.Hash4, rnd(4, 2))]
+    slots += [(ST.Hash8, rnd(8, 3))] + [(ST.Hash8, None)] * 5 + [(ST.Commitment, None)]
+    slots += [(ST.BitDecomp, rnd(1, 4)), (ST.BitDecomp, None), (ST.BitDecomp, None)]
+    blocks = L.generate_slots_witnesses(0, slots)
+    assert sum(b.size for b in blocks) == 7808 * 32          # src/lem/multiframe.rs:503-516 + eval.rs:1966
+    for (st, pre), blk in zip(slots, blocks):
+        pre = pre if pre is not None else [0] * st.preimg_size()
+        if st is ST.BitDecomp:
+            want = oracle.bitdecomp_witness_batch(0, pack(pre))
+        else:
+            want = oracle.poseidon_witness_batch(0, st.preimg_size(), pack(pre))
+        assert np.array_equal(blk, want)

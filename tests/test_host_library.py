@@ -1,0 +1,108 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/lurk_b200.h declares, its host-only
+entry points agree with the oracle, the GPU limb algorithms (compiled for the host with the carry flag emulated)
+agree with Python big-int arithmetic, and compute calls fail loudly without a GPU."""
+import ctypes
+import os
+import random
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import ints, pack
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(L):
+    header = open(os.path.join(ROOT, "include", "lurk_b200.h")).read()
+    declared = set(re.findall(r"\b(lurk_[a-z0-9_]+)\s*\(", header))
+    declared -= {"lurk_dag_node"}
+    assert declared, "no declarations parsed"
+    lib = L._capi.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in L._capi.PROTOTYPES, f"{name} has no ctypes prototype"
+    assert set(L._capi.PROTOTYPES) <= declared
+
+
+def test_compute_fails_loudly_without_gpu(L):
+    if L._capi.lib().lurk_device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(L.LurkError) as e:
+        L.PoseidonCache(0).hash4([1, 2, 3, 4])
+    assert e.value.code == L._capi.ERR_NOGPU
+    with pytest.raises(L.LurkError):
+        L.CommitmentKey(0, np.zeros(64, dtype=np.uint8))
+
+
+@pytest.mark.parametrize("field", [0, 1, 2, 3])
+@pytest.mark.parametrize("arity", [3, 4, 6, 8])
+def test_product_poseidon_constants_match_spec(L, spec, field, arity):
+    # the library generates its constants itself (host C++); the oracle generates them in Python
+    c = L.HashConstants(field).constants(arity)
+    P = spec.params(field, arity)
+    assert (c["full_rounds"], c["partial_rounds"]) == (P["rf"], P["rp"])
+    assert c["round_constants"] == P["rc"]
+    assert c["mds"] == P["mds"]
+
+
+def test_witness_block_sizes(L):
+    ST = L.SlotType
+    assert [L.compute_witness_size(s, 0) for s in (ST.Hash4, ST.Hash6, ST.Hash8, ST.Commitment, ST.BitDecomp)] == [293, 343, 396, 268, 354]
+    assert [L.compute_witness_size(ST.BitDecomp, f) for f in (2, 3, 0, 1)] == [298, 301, 354, 364]   # multiframe.rs:495-498
+
+
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+def test_host_point_sum_and_synthetic_bases(L, oracle, spec, curve):
+    n = 300
+    bases = L.synthetic_bases(curve, n, start=7)
+    assert np.array_equal(bases, oracle.gen_bases(curve, n, start=7))
+    C = spec.CURVES[curve]
+    assert spec.on_curve(curve, (ints(bases)[0], ints(bases)[1]))
+    pts = np.zeros(96 * 5, dtype=np.uint8)
+    for k in range(4):                       # 4 finite points + 1 identity
+        pts[96 * k:96 * k + 64] = bases[64 * k:64 * k + 64]
+        pts[96 * k + 64] = 1
+    assert np.array_equal(L.point_sum(curve, pts), oracle.point_sum(curve, pts))
+    # P + (-P)
+    pb = spec.FIELD_MODULUS[C["base"]]
+    x, y = ints(bases)[0], ints(bases)[1]
+    two = np.concatenate([pack([x, y, 1]), pack([x, pb - y, 1])])
+    assert not L.point_sum(curve, two).any()
+
+
+@pytest.fixture(scope="module", params=["emulated_gpu_limbs", "host_fast_path"])
+def fieldlib(request, tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("fht") / f"libfht_{request.param}.so")
+    flags = ["-DLURK_HOST_EMULATE_CC"] if request.param == "emulated_gpu_limbs" else []
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", *flags, "-I",
+                           os.path.join(ROOT, "lurk-beta_b200", "csrc"), "-x", "c++",
+                           os.path.join(ROOT, "tests", "csrc", "field_host_test.cc"), "-o", out])
+    return ctypes.CDLL(out)
+
+
+@pytest.mark.parametrize("field", [0, 1, 2, 3])
+def test_limb_arithmetic_against_bigints(fieldlib, spec, field):
+    p = spec.FIELD_MODULUS[field]
+    rnd = random.Random(field)
+    cases = [(0, 0), (1, 1), (p - 1, p - 1), (p - 1, 1), (1 << 253, (1 << 253) - 1)]
+    cases += [(rnd.randrange(p), rnd.randrange(p)) for _ in range(400)]
+    ops = {0: lambda a, b: a * b % p, 1: lambda a, b: (a + b) % p, 2: lambda a, b: (a - b) % p,
+           4: lambda a, b: -a % p, 5: lambda a, b: pow(a, 5, p), 6: lambda a, b: a * a % p}
+    out = ctypes.create_string_buffer(32)
+    for a, b in cases:
+        for op, fn in ops.items():
+            assert fieldlib.fe_test_op(field, op, a.to_bytes(32, "little"), b.to_bytes(32, "little"), out) == 0
+            assert int.from_bytes(out.raw, "little") == fn(a, b), (field, op)
+    for a, _ in cases[:12]:
+        fieldlib.fe_test_op(field, 3, a.to_bytes(32, "little"), bytes(32), out)
+        assert int.from_bytes(out.raw, "little") == pow(a, p - 2, p)
+    # lazy dot products (one reduction per MDS row)
+    for trial in range(300):
+        k = rnd.randint(1, 9)
+        A = [p - 1] * k if trial < 5 else [rnd.randrange(p) for _ in range(k)]
+        B = [p - 1] * k if trial < 5 else [rnd.randrange(p) for _ in range(k)]
+        fieldlib.fe_test_dot(field, k, b"".join(x.to_bytes(32, "little") for x in A), b"".join(x.to_bytes(32, "little") for x in B), out)
+        assert int.from_bytes(out.raw, "little") == sum(x * y for x, y in zip(A, B)) % p

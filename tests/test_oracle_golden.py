@@ -1,0 +1,166 @@
+"""Pins the oracle (oracle/spec.py and oracle/oracle.c) on every golden vector the reference's own tests hold for
+the Poseidon path and on the sizes it pins (witness sizes, bit-decomposition sizes)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from util import GOLDEN, TAG_CHAR, TAG_NUM, TAG_STR, TAG_SYM, ints, pack, random_elements
+
+BN = 0
+
+
+def h(oracle, field, pre, mode=1):
+    return ints(oracle.poseidon_hash_batch(field, len(pre), pack(pre), mode=mode))[0]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_trie_goldens(oracle, spec, mode):
+    d = h(oracle, BN, [0] * 8, mode)
+    assert d == GOLDEN["G1"] == spec.hash_correct(BN, [0] * 8)
+    seq = [d]
+    for _ in range(84):
+        seq.append(h(oracle, BN, [seq[-1]] * 8, mode))
+    assert seq[1] == GOLDEN["G2"] and seq[2] == GOLDEN["G3"] and seq[3] == GOLDEN["G4"]
+    assert seq[84] == GOLDEN["G5"]          # empty StandardTrie root = H8 iterated 85 times from 0
+
+
+def test_commitment_goldens(oracle, spec):
+    assert h(oracle, BN, [0, TAG_NUM, 0]) == GOLDEN["G6"] == spec.hash_optimised(BN, [0, TAG_NUM, 0])
+    assert h(oracle, BN, [0, TAG_NUM, 123]) == GOLDEN["G7"]
+
+
+def lurk_str(oracle, s):
+    acc = 0
+    for ch in reversed(s):
+        acc = h(oracle, BN, [TAG_CHAR, ord(ch), TAG_STR, acc])     # src/lem/store.rs:1368-1386
+    return acc
+
+
+def lurk_sym(oracle, path):
+    acc = 0
+    for name in path:
+        acc = h(oracle, BN, [TAG_STR, lurk_str(oracle, name), TAG_SYM, acc])   # src/lem/store.rs:1389-1412
+    return acc
+
+
+def test_nil_commitment_golden_arity4_chain(oracle):
+    nil = lurk_sym(oracle, ["lurk", "nil"])
+    assert h(oracle, BN, [0, 0, nil]) == GOLDEN["G8"]             # (commit nil): Nil tag = 0
+
+
+def test_structural_zero_tuples(oracle, spec):
+    # G12: hash_ptr of tuple2/3/4 of zero atoms equals hash4/6/8 of zeros (src/lem/store.rs:1305-1338)
+    for a in (4, 6, 8):
+        assert h(oracle, BN, [0] * a) == spec.hash_correct(BN, [0] * a)
+
+
+def test_witness_sizes_pinned_by_reference(oracle, spec):
+    # src/lem/multiframe.rs:991-1016 / src/lem/eval.rs:1960-1967: 14*293 + 6*396 + 268 + 3*354 = 7808 (BN256)
+    assert [oracle.witness_block(BN, a) for a in (4, 6, 8, 3)] == [293, 343, 396, 268]
+    assert 14 * 293 + 6 * 396 + 268 + 3 * oracle.bitdecomp_size(BN) == 7808
+    # BIT_DECOMP_*_WITNESS_SIZE, src/lem/multiframe.rs:495-498 (Pallas, Vesta, BN256, Grumpkin)
+    assert [oracle.bitdecomp_size(f) for f in (2, 3, 0, 1)] == [298, 301, 354, 364]
+    assert [len(spec.bitdecomp_witness(f, 5)[0]) for f in (2, 3, 0, 1)] == [298, 301, 354, 364]
+
+
+def test_survey_fingerprints(spec):
+    # digest + sha256 over the aux values of the surveyor's independent probe
+    fp = {
+        (0, (0,) * 8): "1cefe00ba3c2b6ff56990084b0e3c943f0243034f65c1e9a125735d76b0a73f9",
+        (0, (0, 4, 0)): "9f6f2d39663d2a4b585cc22e5274e4a5350a887e5cce2d8f2a6f438fe87bbe6f",
+        (0, (1, 2, 3, 4)): "cd51b69c4f4de87998fd42e74a84fd9ab1aaffd0a7586133f2ee91ee21b1b5cd",
+        (2, (0,) * 8): "2987485991fa415a02592a614b658cb4f604cb0ecec2f0584a3c12f6e64f6ec1",
+        (2, (1, 2, 3, 4)): "dd957ded87f617df3015ec08a4937f40085748d7a72026f09a15de9068cd1530",
+    }
+    for (f, pre), want in fp.items():
+        _, aux = spec.hash_optimised(f, list(pre), True)
+        assert hashlib.sha256(b"".join(spec.fe_to_bytes(a) for a in aux)).hexdigest() == want
+    assert spec.hash_correct(2, [0] * 8) == 0x0ef417527046e53c528056fe84bb984683b4610d346c2a33a81830c13a876b1c
+
+
+@pytest.mark.parametrize("field", [0, 1, 2, 3])
+@pytest.mark.parametrize("arity", [3, 4, 6, 8])
+def test_c_oracle_matches_python_spec(oracle, spec, field, arity):
+    pre = random_elements(field, 3 * arity, seed=100 + 10 * field + arity)
+    rows = [ints(pre)[i * arity:(i + 1) * arity] for i in range(3)]
+    d0 = ints(oracle.poseidon_hash_batch(field, arity, pre, mode=0))
+    d1 = ints(oracle.poseidon_hash_batch(field, arity, pre, mode=1))
+    w = ints(oracle.poseidon_witness_batch(field, arity, pre))
+    blk = oracle.witness_block(field, arity)
+    for i, r in enumerate(rows):
+        assert d0[i] == d1[i] == spec.hash_correct(field, r)
+        assert w[i * blk:(i + 1) * blk] == spec.slot_witness(field, r)
+
+
+@pytest.mark.parametrize("field", [0, 1, 2, 3])
+def test_bitdecomp_oracle(oracle, spec, field):
+    p = spec.FIELD_MODULUS[field]
+    vals = [0, 1, 2, p - 1, p // 2, (1 << 64) - 1] + ints(random_elements(field, 4, seed=7))
+    w = ints(oracle.bitdecomp_witness_batch(field, pack(vals)))
+    size = oracle.bitdecomp_size(field)
+    for i, v in enumerate(vals):
+        aux, bits = spec.bitdecomp_witness(field, v)
+        assert w[i * size:(i + 1) * size] == aux
+        assert sum(b << k for k, b in enumerate(bits)) == v
+
+
+def test_noncanonical_rejected(oracle, spec):
+    bad = pack([spec.FIELD_MODULUS[0]] + [0] * 7)
+    with pytest.raises(ValueError):
+        oracle.poseidon_hash_batch(0, 8, bad)
+
+
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+def test_msm_oracle(oracle, spec, curve):
+    C = spec.CURVES[curve]
+    pb, q = spec.FIELD_MODULUS[C["base"]], spec.FIELD_MODULUS[C["scalar"]]
+    assert spec.on_curve(curve, C["gen"])
+    n = 24
+    bases = oracle.gen_bases(curve, n)
+    pts = list(zip(ints(bases)[0::2], ints(bases)[1::2]))
+    assert pts[6] == spec.ec_mul(7, C["gen"], pb)
+    sc = ints(random_elements(C["scalar"], n, seed=3))
+    sc[0], sc[1], sc[2] = 0, 1, q - 1
+    want = spec.msm_naive(curve, pts, sc)
+    for naive in (True, False):
+        o = oracle.msm(curve, bases, pack(sc), nthreads=2, naive=naive)
+        assert (ints(o[:64])[0], ints(o[:64])[1]) == want and o[64] == 1
+    # identity result
+    o = oracle.msm(curve, bases, pack([0] * n))
+    assert not o.any()
+
+
+@pytest.mark.parametrize("field", [0, 2, 3])
+def test_ntt_oracle(oracle, spec, field):
+    a = ints(random_elements(field, 16, seed=9))
+    got = oracle.ntt(field, pack(a))
+    assert ints(got) == spec.ntt_naive(field, a)
+    assert ints(oracle.ntt(field, got, inverse=True)) == a
+
+
+def test_fold_helpers_oracle(oracle, spec):
+    f, p = 0, spec.FIELD_MODULUS[0]
+    a, b = ints(random_elements(f, 8, 1)), ints(random_elements(f, 8, 2))
+    r = 0x1234567890abcdef1234567890abcdef
+    assert ints(oracle.axpy(f, pack(a), pack(b), pack([r]))) == [(x + r * y) % p for x, y in zip(a, b)]
+    row_ptr, col, val = [0, 2, 2, 5], [0, 3, 1, 2, 7], [3, p - 1, 5, 7, 11]
+    y = ints(oracle.spmv(f, row_ptr, col, pack(val), pack(a)))
+    assert y == [(3 * a[0] + (p - 1) * a[3]) % p, 0, (5 * a[1] + 7 * a[2] + 11 * a[7]) % p]
+    v = [ints(random_elements(f, 4, 10 + k)) for k in range(6)]
+    u1, u2 = 77, 1
+    t = ints(oracle.cross_term(f, *[pack(x) for x in v], pack([u1]), pack([u2])))
+    assert t == [(v[0][i] * v[4][i] + v[3][i] * v[1][i] - u1 * v[5][i] - u2 * v[2][i]) % p for i in range(4)]
+
+
+def test_dag_oracle_matches_flat_hashes(oracle, spec):
+    # tuple2 of (atom0, atom1) then a compact and a commitment over it (src/lem/store.rs:29-78 layouts)
+    atoms = pack([11, 22, 33])
+    nodes = np.zeros(3, dtype=oracle.DAG_NODE)
+    nodes[0] = (2, 0, [5, 6, 0, 0], [0, 1, 0, 0])
+    nodes[1] = (5, 0, [9, 7, 9, 9], [2, 3, 0, 0])      # compact: children atom2, node0, atom0; tags 0 and 2 dropped
+    nodes[2] = (6, 0, [0, 4, 0, 0], [1, 4, 0, 0])      # commitment: secret atom1, payload (tag 4, node1)
+    out = ints(oracle.dag_hash(0, nodes, atoms))
+    d0 = spec.hash_correct(0, [5, 11, 6, 22])
+    d1 = spec.hash_correct(0, [33, 7, d0, 11])
+    assert out == [d0, d1, spec.hash_correct(0, [22, 4, d1])]
