@@ -129,6 +129,10 @@ void lurk_msm_ctx_destroy(lurk_msm_ctx *ctx);
 int lurk_msm_ctx_run(lurk_msm_ctx *ctx, const uint8_t *scalars, size_t n, int fmt, uint8_t out_xyz[96]);
 int lurk_msm_ctx_run_dev(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, uint8_t out_xyz[96],
                          void *stream);
+/* Measurement hooks: when enabled, every run records CUDA events around the bucket-accumulation kernel (the dominant
+ * kernel) on the launching stream; last_profile returns its duration and the number of kernels the run launched. */
+int lurk_msm_ctx_set_profiling(lurk_msm_ctx *ctx, int enable);
+int lurk_msm_ctx_last_profile(lurk_msm_ctx *ctx, float *accumulate_ms, unsigned *kernel_launches);
 /* one-shot convenience (uploads bases every call) */
 int lurk_msm(int curve_id, const uint8_t *bases_affine, const uint8_t *scalars, size_t n, int fmt,
              uint8_t out_xyz[96]);

@@ -46,6 +46,15 @@ class CommitmentKey:
         _capi.check(_capi.lib().lurk_msm_ctx_run_dev(self._ctx, C.c_void_p(d_scalars_ptr), n, fmt, _capi.np_ptr(out), C.c_void_p(stream)))
         return out
 
+    def set_profiling(self, enable=True):
+        _capi.check(_capi.lib().lurk_msm_ctx_set_profiling(self._ctx, 1 if enable else 0))
+
+    def last_profile(self):
+        """(device ms of the bucket-accumulation kernel, kernels launched) of the last run"""
+        ms, k = C.c_float(), C.c_uint()
+        _capi.check(_capi.lib().lurk_msm_ctx_last_profile(self._ctx, C.byref(ms), C.byref(k)))
+        return ms.value, k.value
+
     def close(self):
         if getattr(self, "_ctx", None) and self._ctx.value:
             _capi.lib().lurk_msm_ctx_destroy(self._ctx)

@@ -298,6 +298,11 @@ struct lurk_msm_ctx {
     bool owns_bases = false;
     std::mutex mu;
     MsmScratch scratch;
+    // optional device timing of the dominant kernel (bucket accumulation), on the launching stream
+    bool profile = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_accumulate_ms = 0.f;
+    unsigned last_launches = 0;
 };
 
 namespace lurk {
@@ -349,8 +354,11 @@ static int msm_run(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, 
     msm_count_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, P.nb, counts);
     msm_scan_kernel<<<1, 1024, 0, s>>>(counts, TB, offsets);
     msm_scatter_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, P.nb, offsets, cursor, sorted);
+    if (ctx->profile) cudaEventRecord(ctx->ev0, s);
     msm_accumulate_kernel<Fb><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, (const Affine<Fb> *)ctx->d_bases, buckets,
                                                                 S.pkey[0].as<uint32_t>(), S.ppt[0].as<Pt>(), P.seg, P.t1);
+    if (ctx->profile) cudaEventRecord(ctx->ev1, s);
+    unsigned launches = 4;
     // shrinking passes over the partial list
     uint32_t count = P.t1;
     int cur = 0;
@@ -360,16 +368,19 @@ static int msm_run(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, 
         const int last = threads == 1;
         msm_partial_kernel<Fb><<<(threads + 127) / 128, 128, 0, s>>>(S.pkey[cur].as<uint32_t>(), S.ppt[cur].as<Pt>(), count, buckets,
                                                                     S.pkey[cur ^ 1].as<uint32_t>(), S.ppt[cur ^ 1].as<Pt>(), seg2, last);
+        launches++;
         if (last) break;
         count = threads;
         cur ^= 1;
     }
+    ctx->last_launches = launches + 2;
     const uint32_t nchunks = TB / P.chunk;
     msm_bucket_reduce_kernel<Fb><<<(nchunks + 127) / 128, 128, 0, s>>>(buckets, P.nb, P.chunk, nchunks, S.chunks.as<Pt>());
     msm_window_sum_kernel<Fb><<<P.nwin, 256, 0, s>>>(S.chunks.as<Pt>(), P.nb / P.chunk, S.wins.as<Pt>());
     LURK_CUDA_TRY(cudaGetLastError());
     LURK_CUDA_TRY(cudaMemcpyAsync(S.h_wins, S.wins.p, (size_t)P.nwin * sizeof(Pt), cudaMemcpyDeviceToHost, s));
     LURK_CUDA_TRY(cudaStreamSynchronize(s));
+    if (ctx->profile) cudaEventElapsedTime(&ctx->last_accumulate_ms, ctx->ev0, ctx->ev1);
     // Horner over the windows on the host
     const Pt *w = reinterpret_cast<const Pt *>(S.h_wins);
     Pt acc = Pt::identity();
@@ -427,8 +438,26 @@ int lurk_msm_ctx_create(int curve_id, const uint8_t *bases_affine, size_t n, int
     return rc;
 }
 
+int lurk_msm_ctx_set_profiling(lurk_msm_ctx *ctx, int enable) {
+    if (!ctx) { set_error("null context"); return LURK_ERR_ARG; }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (enable && !ctx->ev0) {
+        LURK_CUDA_TRY(cudaEventCreate(&ctx->ev0));
+        LURK_CUDA_TRY(cudaEventCreate(&ctx->ev1));
+    }
+    ctx->profile = enable != 0;
+    return LURK_OK;
+}
+int lurk_msm_ctx_last_profile(lurk_msm_ctx *ctx, float *accumulate_ms, unsigned *kernel_launches) {
+    if (!ctx) { set_error("null context"); return LURK_ERR_ARG; }
+    if (accumulate_ms) *accumulate_ms = ctx->last_accumulate_ms;
+    if (kernel_launches) *kernel_launches = ctx->last_launches;
+    return LURK_OK;
+}
+
 void lurk_msm_ctx_destroy(lurk_msm_ctx *ctx) {
     if (!ctx) return;
+    if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     if (ctx->owns_bases && ctx->d_bases) cudaFree(ctx->d_bases);
     delete ctx;
 }

@@ -115,7 +115,8 @@ def test_fold_helpers_parity(L, oracle, spec, field):
     p = spec.FIELD_MODULUS[field]
     val = pack([[1, p - 1, 2, 5, 7, (1 << 64) + 3][k] for k in rng.integers(0, 6, size=col.size)])
     y = torch.empty(rows * 32, dtype=torch.uint8, device="cuda")
-    L._capi.check(lib.lurk_spmv_csr_dev(field, dev(row_ptr).data_ptr(), dev(col).data_ptr(), dev(mont(spec, field, val)).data_ptr(),
+    d_rp, d_col, d_val = dev(row_ptr), dev(col), dev(mont(spec, field, val))     # keep the device buffers alive
+    L._capi.check(lib.lurk_spmv_csr_dev(field, d_rp.data_ptr(), d_col.data_ptr(), d_val.data_ptr(),
                                         rows, da.data_ptr(), y.data_ptr(), None))
     assert unmont(spec, field, y.cpu().numpy()) == ints(oracle.spmv(field, row_ptr, col, val, a))
     # cross term
