@@ -65,6 +65,10 @@ if __name__ == "__main__":
             poseidon(f, a, ln)
         for ln in (8, 11):
             poseidon(0, 4, ln)
+    if which == "poseidon8":
+        poseidon(0, 8, 20)
+    if which == "msm21":
+        msm(0, 21, "witness")
     if which in ("all", "msm"):
         for c, ln, sh in [(0, 16, "uniform"), (0, 20, "uniform"), (0, 20, "witness"), (2, 20, "uniform"), (0, 21, "witness")]:
             msm(c, ln, sh)
