@@ -489,46 +489,57 @@ int oracle_msm_naive(int curve_id, const uint8_t *bases, const uint8_t *scalars,
     return 0;
 }
 
-/* Pippenger, unsigned windows, OpenMP over windows (the shape of a CPU vartime MSM) */
+/* Pippenger, unsigned windows; OpenMP over (window, chunk-of-points) tasks so that all host threads are busy
+ * (the shape of a multi-threaded CPU vartime MSM).  Window width minimises nwin * (n + chunks * 2^(c+1)). */
 int oracle_msm_pippenger(int curve_id, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t out[96],
                          int nthreads) {
     init_fields();
     const fctx *f = &F[CURVE_BASE[curve_id]];
-    int c = 3;
-    if (n >= 32) { c = 0; size_t m = n; while (m >>= 1) c++; c = c * 69 / 100 + 2; }
-    if (c > 16) c = 16;
-    int nwin = (256 + c - 1) / c;
+    if (nthreads < 1) nthreads = 1;
+    int c = 4, chunks = 1;
+    double best = -1;
+    for (int cc = 3; cc <= 16; cc++) {
+        int nw = (255 + cc - 1) / cc;
+        int ch = (nthreads + nw - 1) / nw;
+        if (ch < 1) ch = 1;
+        if ((size_t)ch > n / 64 + 1) ch = (int)(n / 64 + 1);
+        double cost = (double)nw * ((double)n + (double)ch * (double)((size_t)2 << cc));
+        if (best < 0 || cost < best) { best = cost; c = cc; chunks = ch; }
+    }
+    int nwin = (255 + c - 1) / c;
     fe *bx = malloc(sizeof(fe) * (n + 1)), *by = malloc(sizeof(fe) * (n + 1));
     if (load_bases(f, bases, n, bx, by)) { free(bx); free(by); return -3; }
-    jac *wsum = calloc(nwin, sizeof(jac));
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads > 0 ? nthreads : 1)
-    for (int w = 0; w < nwin; w++) {
+    int ntasks = nwin * chunks;
+    jac *part = calloc(ntasks, sizeof(jac));
+    size_t per = (n + chunks - 1) / chunks;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+    for (int task = 0; task < ntasks; task++) {
+        int w = task / chunks, ch = task % chunks;
+        size_t lo = (size_t)ch * per, hi = lo + per < n ? lo + per : n;
         size_t nb = ((size_t)1 << c) - 1;
         jac *bk = calloc(nb, sizeof(jac));
-        for (size_t i = 0; i < n; i++) {
-            const uint8_t *k = scalars + 32 * i;
-            uint64_t lo[4]; memcpy(lo, k, 32);
+        for (size_t i = lo; i < hi; i++) {
+            uint64_t k[4]; memcpy(k, scalars + 32 * i, 32);
             int bit = w * c;
-            uint64_t d = lo[bit / 64] >> (bit % 64);
-            if ((bit % 64) + c > 64 && bit / 64 < 3) d |= lo[bit / 64 + 1] << (64 - bit % 64);
+            uint64_t d = k[bit / 64] >> (bit % 64);
+            if ((bit % 64) + c > 64 && bit / 64 < 3) d |= k[bit / 64 + 1] << (64 - bit % 64);
             d &= ((uint64_t)1 << c) - 1;
-            if (bit >= 256) d = 0;
             if (!d) continue;
             jac p; j_from_affine(f, &p, &bx[i], &by[i]);
             j_add(f, &bk[d - 1], &bk[d - 1], &p);
         }
         jac run, sum; memset(&run, 0, sizeof run); memset(&sum, 0, sizeof sum);
         for (size_t b = nb; b-- > 0;) { j_add(f, &run, &run, &bk[b]); j_add(f, &sum, &sum, &run); }
-        wsum[w] = sum;
+        part[task] = sum;
         free(bk);
     }
     jac acc; memset(&acc, 0, sizeof acc);
     for (int w = nwin - 1; w >= 0; w--) {
         for (int i = 0; i < c; i++) j_dbl(f, &acc, &acc);
-        j_add(f, &acc, &acc, &wsum[w]);
+        for (int ch = 0; ch < chunks; ch++) j_add(f, &acc, &acc, &part[w * chunks + ch]);
     }
     j_to_affine_bytes(f, out, &acc);
-    free(bx); free(by); free(wsum);
+    free(bx); free(by); free(part);
     return 0;
 }
 
