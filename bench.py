@@ -179,42 +179,83 @@ class FoldStepGPU:
 
     def stage_inputs(self):
         """host -> device copy of this step's inputs from pinned memory (the e2e leg)"""
+        if getattr(self, "ev_fold", None) is not None:
+            self.torch.cuda.current_stream().wait_event(self.ev_fold)   # W2's glue region is still read by the last fold
         for arity, t in self.slot_pre_host.items():
             self.slot_pre_dev[arity].copy_(t, non_blocking=True)
         self.bd_dev.copy_(self.bd_host, non_blocking=True)
         self.W2[self.slot_region * 32:].copy_(self.glue_host, non_blocking=True)
 
+    def _streams(self):
+        if not hasattr(self, "sK"):
+            t = self.torch
+            self.sK = [t.cuda.Stream() for _ in range(3)]      # slot-witness kernels, one stream per arity
+            self.sB = t.cuda.Stream()                          # SpMV / cross term / commit(T) / fold
+            self.sS = t.cuda.Stream()                          # secondary-circuit commitments
+            self.ckT = self.ck.clone()
+            self.ckT.set_profiling(True)
+            self.ck2b = self.ck2.clone()
+            self.ev_fold = None
+        return self.sK, self.sB, self.sS
+
     def step(self, group=None):
-        L, lib, chk = self.L, self.lib, self.L._capi.check
+        """One fold.  Independent pieces run on separate streams so the latency-bound tails of one commitment
+        (partial passes, bucket reduce, read-back) overlap the multiply-bound kernels of the other."""
+        L, lib, chk, t = self.L, self.lib, self.L._capi.check, self.torch
         M = L.FMT_MONTGOMERY
+        sK, sB, sS = self._streams()
         k = 0
-        # K3: slot witnesses straight into W2 (Montgomery in, Montgomery out)
-        for arity, n, off, blk in self.slot_layout:
+        cur = t.cuda.current_stream()
+        for st in (*sK, sB, sS):
+            st.wait_stream(cur)                                # inputs staged on the current stream
+        if self.ev_fold is not None:
+            for st in sK:
+                st.wait_event(self.ev_fold)                    # W2 is read by the previous step's fold
+        # K3: slot witnesses straight into W2 (Montgomery in, Montgomery out), one stream per slot type
+        evs = []
+        for (arity, n, off, blk), st in zip(self.slot_layout, sK):
             chk(lib.lurk_poseidon_witness_batch_dev(FIELD, arity, self.slot_pre_dev[arity].data_ptr(), n,
-                                                    self.W2.data_ptr() + off * 32, M, None)); k += 1
-        chk(lib.lurk_bitdecomp_witness_batch_dev(FIELD, self.bd_dev.data_ptr(), self.bd_n, self.W2.data_ptr() + self.bd_off * 32, M, None)); k += 1
-        # K4: comm_W (partial over this rank's key shard)
-        cw = self.ck.commit_device(self.W2.data_ptr(), self.nW, fmt=M)
-        ms, kl = self.ck.last_profile(); self.acc_ms.append(ms); k += kl
-        # K5: Az, Bz, Cz for both instances, cross term
+                                                    self.W2.data_ptr() + off * 32, M, C.c_void_p(st.cuda_stream))); k += 1
+        chk(lib.lurk_bitdecomp_witness_batch_dev(FIELD, self.bd_dev.data_ptr(), self.bd_n, self.W2.data_ptr() + self.bd_off * 32, M,
+                                                 C.c_void_p(sK[2].cuda_stream))); k += 1
+        for st in sK:
+            e = t.cuda.Event(); e.record(st); evs.append(e)
+        # K4: comm_W (partial over this rank's key shard) -- enqueue only
+        sK[0].wait_event(evs[1]); sK[0].wait_event(evs[2])
+        self.ck.launch_device(self.W2.data_ptr(), self.nW, fmt=M, stream=sK[0].cuda_stream)
+        # K5 on sB: Az1,Bz1,Cz1 need only the running instance; Az2.. wait for the slot witnesses
         nb = self.nW * 32
-        self.z1[:nb].copy_(self.W1, non_blocking=True)
-        self.z2[:nb].copy_(self.W2, non_blocking=True)
+        sb = C.c_void_p(sB.cuda_stream)
+        with t.cuda.stream(sB):
+            self.z1[:nb].copy_(self.W1, non_blocking=True)
         for i, (rp, col, val, _nnz) in enumerate(self.mats):
-            for j, z in enumerate((self.z1, self.z2)):
-                chk(lib.lurk_spmv_csr_dev(FIELD, rp.data_ptr(), col.data_ptr(), val.data_ptr(), self.nT, z.data_ptr(),
-                                          self.mv[2 * i + j].data_ptr(), None)); k += 1
+            chk(lib.lurk_spmv_csr_dev(FIELD, rp.data_ptr(), col.data_ptr(), val.data_ptr(), self.nT, self.z1.data_ptr(),
+                                      self.mv[2 * i].data_ptr(), sb)); k += 1
+        for e in evs:
+            sB.wait_event(e)
+        with t.cuda.stream(sB):
+            self.z2[:nb].copy_(self.W2, non_blocking=True)
+        for i, (rp, col, val, _nnz) in enumerate(self.mats):
+            chk(lib.lurk_spmv_csr_dev(FIELD, rp.data_ptr(), col.data_ptr(), val.data_ptr(), self.nT, self.z2.data_ptr(),
+                                      self.mv[2 * i + 1].data_ptr(), sb)); k += 1
         az1, az2, bz1, bz2, cz1, cz2 = self.mv
         chk(lib.lurk_cross_term_dev(FIELD, az1.data_ptr(), bz1.data_ptr(), cz1.data_ptr(), az2.data_ptr(), bz2.data_ptr(), cz2.data_ptr(),
-                                    L._capi.np_ptr(self.u1), L._capi.np_ptr(self.u2), self.nT, self.T.data_ptr(), None)); k += 1
+                                    L._capi.np_ptr(self.u1), L._capi.np_ptr(self.u2), self.nT, self.T.data_ptr(), sb)); k += 1
         # K4: comm_T
-        ct = self.ck.commit_device(self.T.data_ptr(), self.nT, fmt=M)
+        self.ckT.launch_device(self.T.data_ptr(), self.nT, fmt=M, stream=sB.cuda_stream)
+        # secondary circuit (Grumpkin): two small commitments
+        self.ck2.launch_device(self.W_sec.data_ptr(), SECONDARY_N, fmt=M, stream=sS.cuda_stream)
+        self.ck2b.launch_device(self.T_sec.data_ptr(), SECONDARY_N, fmt=M, stream=sS.cuda_stream)
+        # collect
+        cw = self.ck.finish()
         ms, kl = self.ck.last_profile(); self.acc_ms.append(ms); k += kl
+        ct = self.ckT.finish()
+        ms, kl = self.ckT.last_profile(); self.acc_ms.append(ms); k += kl
         # exchange: the two partial commitments (all-gather + local adds; nothing to do on one GPU)
         if self.world > 1:
             import torch.distributed as dist
-            mine = self.torch.from_numpy(np.concatenate([cw, ct])).cuda()
-            allp = self.torch.empty(192 * self.world, dtype=self.torch.uint8, device="cuda")
+            mine = t.from_numpy(np.concatenate([cw, ct])).cuda()
+            allp = t.empty(192 * self.world, dtype=t.uint8, device="cuda")
             dist.all_gather_into_tensor(allp, mine, group=group)
             allp = allp.cpu().numpy().reshape(self.world, 2, 96)
             cw = L.point_sum(CURVE, allp[:, 0, :].reshape(-1), fmt=M)
@@ -222,13 +263,13 @@ class FoldStepGPU:
         # challenge r (stand-in for the Poseidon-sponge RO on the CPU: 128 bits derived from the commitments)
         r = np.zeros(32, dtype=np.uint8)
         r[:16] = np.frombuffer(hashlib.sha256(cw.tobytes() + ct.tobytes()).digest()[:16], dtype=np.uint8)
-        # K5: fold
-        chk(lib.lurk_axpy_dev(FIELD, self.W1.data_ptr(), self.W2.data_ptr(), L._capi.np_ptr(r), self.nW, self.W1.data_ptr(), None)); k += 1
-        chk(lib.lurk_axpy_dev(FIELD, self.E1.data_ptr(), self.T.data_ptr(), L._capi.np_ptr(r), self.nT, self.E1.data_ptr(), None)); k += 1
-        # secondary circuit (Grumpkin): two small commitments
-        for v in (self.W_sec, self.T_sec):
-            self.ck2.commit_device(v.data_ptr(), SECONDARY_N, fmt=M)
-            k += self.ck2.last_profile()[1]
+        # K5: fold (on sB, after commit(T); W2 is free again once this is done)
+        chk(lib.lurk_axpy_dev(FIELD, self.W1.data_ptr(), self.W2.data_ptr(), L._capi.np_ptr(r), self.nW, self.W1.data_ptr(), sb)); k += 1
+        chk(lib.lurk_axpy_dev(FIELD, self.E1.data_ptr(), self.T.data_ptr(), L._capi.np_ptr(r), self.nT, self.E1.data_ptr(), sb)); k += 1
+        self.ev_fold = t.cuda.Event(); self.ev_fold.record(sB)
+        self.ck2.finish(); k += self.ck2.last_profile()[1]
+        self.ck2b.finish(); k += self.ck2b.last_profile()[1]
+        cur.wait_stream(sB)                                    # the step ends when the fold is enqueued behind it
         self.launches = k
         self.d2h_bytes = 2 * 96 + 4 * 16 * 128        # result points + window sums read back by the 4 commitments
         return cw, ct
@@ -256,6 +297,7 @@ def run_gpu(args):
         e0.record()
         for _ in range(steps):
             fn()
+        torch.cuda.synchronize()          # work runs on several streams: close the region after all of them drained
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")

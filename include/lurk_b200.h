@@ -129,6 +129,12 @@ void lurk_msm_ctx_destroy(lurk_msm_ctx *ctx);
 int lurk_msm_ctx_run(lurk_msm_ctx *ctx, const uint8_t *scalars, size_t n, int fmt, uint8_t out_xyz[96]);
 int lurk_msm_ctx_run_dev(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, uint8_t out_xyz[96],
                          void *stream);
+/* Asynchronous form: `launch` enqueues the whole commitment on `stream` and returns; `finish` waits for it and
+ * produces the point.  One launch may be pending per context; `clone` gives another context on the same resident key
+ * (own scratch; the parent must outlive it) so that e.g. commit(W) and commit(T) of one fold overlap. */
+int lurk_msm_ctx_launch_dev(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, void *stream);
+int lurk_msm_ctx_finish(lurk_msm_ctx *ctx, uint8_t out_xyz[96]);
+int lurk_msm_ctx_clone(lurk_msm_ctx *ctx, lurk_msm_ctx **out);
 /* Measurement hooks: when enabled, every run records CUDA events around the bucket-accumulation kernel (the dominant
  * kernel) on the launching stream; last_profile returns its duration and the number of kernels the run launched. */
 int lurk_msm_ctx_set_profiling(lurk_msm_ctx *ctx, int enable);

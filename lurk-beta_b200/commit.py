@@ -46,6 +46,23 @@ class CommitmentKey:
         _capi.check(_capi.lib().lurk_msm_ctx_run_dev(self._ctx, C.c_void_p(d_scalars_ptr), n, fmt, _capi.np_ptr(out), C.c_void_p(stream)))
         return out
 
+    def launch_device(self, d_scalars_ptr, n, fmt=_capi.FMT_MONTGOMERY, stream=0):
+        """enqueue a commitment on `stream`; pair with finish()"""
+        _capi.check(_capi.lib().lurk_msm_ctx_launch_dev(self._ctx, C.c_void_p(d_scalars_ptr), n, fmt, C.c_void_p(stream)))
+
+    def finish(self):
+        out = np.zeros(96, dtype=np.uint8)
+        _capi.check(_capi.lib().lurk_msm_ctx_finish(self._ctx, _capi.np_ptr(out)))
+        return out
+
+    def clone(self):
+        """another context on the same device-resident key (own scratch), for overlapping commitments"""
+        other = CommitmentKey.__new__(CommitmentKey)
+        other.curve_id, other.n, other._parent = self.curve_id, self.n, self
+        other._ctx = C.c_void_p()
+        _capi.check(_capi.lib().lurk_msm_ctx_clone(self._ctx, C.byref(other._ctx)))
+        return other
+
     def set_profiling(self, enable=True):
         _capi.check(_capi.lib().lurk_msm_ctx_set_profiling(self._ctx, 1 if enable else 0))
 

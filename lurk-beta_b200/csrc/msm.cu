@@ -5,7 +5,8 @@
 // The commitment key is fixed per (rc, Lang) (src/proof/nova.rs:196-216), so it is uploaded once into a context and
 // kept in HBM in Montgomery affine form (64 B / point); every call streams 32 B scalars.
 //
-// Pipeline (all on one stream, no host synchronisation before the final 2 KB read-back):
+// Pipeline (all on one stream, no host synchronisation before the final 2 KB read-back; launch and finish are
+// separate entry points so that independent commitments overlap):
 //   1. digits+histogram: one thread per scalar; signed c-bit windows (buckets 1..2^(c-1), sign folded into the point);
 //      warp-aggregated atomics (__match_any_sync) so the 0/1-heavy witness vectors do not serialise on
 //      one counter.
@@ -92,15 +93,14 @@ __global__ void __launch_bounds__(256) msm_count_kernel(const Fs *__restrict__ s
     }
 }
 
-// single-CTA exclusive scan: offsets[0..len] (offsets[len] = total)
-__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t *__restrict__ counts, uint32_t len, uint32_t *__restrict__ offsets) {
+// ---- exclusive scan of the bucket counts: offsets[0..len], offsets[len] = total.
+// Three small launches: per-CTA sums of 4096 counts, one CTA scanning the <= 2048 CTA sums, per-CTA scan with carry-in.
+static constexpr uint32_t SCAN_TILE = 4096;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t sum, uint32_t *total) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry_s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t per = (len + blockDim.x - 1) / blockDim.x;
-    const uint32_t b = tid * per, e = min(b + per, len);
-    uint32_t sum = 0;
-    for (uint32_t i = b; i < e; i++) sum += counts[i];
     uint32_t incl = sum;
     for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
     if (lane == 31) warp_sums[wid] = incl;
@@ -112,9 +112,41 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t *__restri
         if (lane == 31) carry_s = wi;
     }
     __syncthreads();
-    uint32_t run = warp_sums[wid] + incl - sum;
-    for (uint32_t i = b; i < e; i++) { offsets[i] = run; run += counts[i]; }
-    if (tid == 0) offsets[len] = carry_s;
+    if (total) *total = carry_s;
+    return warp_sums[wid] + incl - sum;
+}
+
+__global__ void __launch_bounds__(1024) msm_scan_tile_sums_kernel(const uint32_t *__restrict__ counts, uint32_t len, uint32_t *__restrict__ tile_sums) {
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (base + k < len) sum += counts[base + k];
+    uint32_t total;
+    block_exclusive_scan_1024(sum, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// one CTA: tile_offsets[0..ntiles] from tile_sums (ntiles <= 4096)
+__global__ void __launch_bounds__(1024) msm_scan_tiles_kernel(const uint32_t *__restrict__ tile_sums, uint32_t ntiles, uint32_t *__restrict__ tile_offsets) {
+    const uint32_t base = threadIdx.x * 4;
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = base + k < ntiles ? tile_sums[base + k] : 0; sum += v[k]; }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan_1024(sum, &total);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (base + k < ntiles) tile_offsets[base + k] = run; run += v[k]; }
+    if (threadIdx.x == 0) tile_offsets[ntiles] = total;
+}
+__global__ void __launch_bounds__(1024) msm_scan_apply_kernel(const uint32_t *__restrict__ counts, uint32_t len, const uint32_t *__restrict__ tile_offsets,
+                                                              uint32_t ntiles, uint32_t *__restrict__ offsets) {
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = base + k < len ? counts[base + k] : 0; sum += v[k]; }
+    uint32_t run = tile_offsets[blockIdx.x] + block_exclusive_scan_1024(sum, nullptr);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (base + k < len) offsets[base + k] = run; run += v[k]; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) offsets[len] = tile_offsets[ntiles];
 }
 
 template <class Fs>
@@ -237,6 +269,48 @@ __global__ void __launch_bounds__(128) msm_partial_kernel(const uint32_t *__rest
     if (!wrote_out && !last_level) keys_out[u] = KEY_NONE;
 }
 
+template <class Fb>
+__device__ __forceinline__ XYZZ<Fb> shfl_up_xyzz(const XYZZ<Fb> &p, int d) {
+    XYZZ<Fb> r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.x.v[i] = __shfl_up_sync(0xffffffffu, p.x.v[i], d);
+        r.y.v[i] = __shfl_up_sync(0xffffffffu, p.y.v[i], d);
+        r.zz.v[i] = __shfl_up_sync(0xffffffffu, p.zz.v[i], d);
+        r.zzz.v[i] = __shfl_up_sync(0xffffffffu, p.zzz.v[i], d);
+    }
+    return r;
+}
+
+// Later levels are latency-bound (few entries): one warp takes 32 consecutive (key, point) entries and combines equal
+// keys with a segmented Hillis-Steele scan over shuffles -- 5 dependent additions per 32x shrink instead of 32.
+template <class Fb>
+__global__ void __launch_bounds__(128) msm_partial_warp_kernel(const uint32_t *__restrict__ keys_in, const XYZZ<Fb> *__restrict__ pts_in,
+                                                               uint32_t count, XYZZ<Fb> *__restrict__ bucket_acc, uint32_t *__restrict__ keys_out,
+                                                               XYZZ<Fb> *__restrict__ pts_out, int last_level) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if ((uint64_t)gw * 32 >= count) return;   // whole warp out of range
+    const uint32_t i = gw * 32 + lane;
+    const uint32_t key = i < count ? keys_in[i] : KEY_NONE;
+    XYZZ<Fb> pt = XYZZ<Fb>::identity();
+    if (key != KEY_NONE) pt = load_xyzz(pts_in + i);
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t k2 = __shfl_up_sync(0xffffffffu, key, d);
+        const XYZZ<Fb> p2 = shfl_up_xyzz(pt, d);
+        if (lane >= (uint32_t)d && k2 == key && key != KEY_NONE) pt.add(p2);
+    }
+    const uint32_t first_key = __shfl_sync(0xffffffffu, key, 0);
+    const uint32_t next_key = __shfl_down_sync(0xffffffffu, key, 1);
+    const bool run_end = key != KEY_NONE && (lane == 31 || next_key != key);
+    if (run_end) {
+        if (key == first_key && !last_level) { keys_out[gw] = key; store_xyzz(pts_out + gw, pt); }
+        else { XYZZ<Fb> b = load_xyzz(bucket_acc + key); b.add(pt); store_xyzz(bucket_acc + key, b); }
+    }
+    if (first_key == KEY_NONE && lane == 0 && !last_level) keys_out[gw] = KEY_NONE;
+}
+
 // per chunk of `chunk` buckets [b0, b0+chunk) of window w:  sum_b (b+1) B_b = tri + b0 * S
 template <class Fb>
 __global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(const XYZZ<Fb> *__restrict__ bucket_acc, uint32_t nb, uint32_t chunk,
@@ -281,7 +355,7 @@ __global__ void __launch_bounds__(256) msm_bases_to_mont_kernel(Fb *coords, size
 
 // ----------------------------------------------------------------------------- context
 struct MsmScratch {
-    DevBuf counts, offsets, sorted, buckets, pkey[2], ppt[2], chunks, wins, scalars;
+    DevBuf counts, offsets, tiles, sorted, buckets, pkey[2], ppt[2], chunks, wins, scalars;
     void *h_wins = nullptr;   // pinned
     ~MsmScratch() { if (h_wins) cudaFreeHost(h_wins); }
 };
@@ -303,6 +377,10 @@ struct lurk_msm_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_accumulate_ms = 0.f;
     unsigned last_launches = 0;
+    // launch / finish split
+    bool pending = false;
+    int pending_fmt = 0, pending_c = 0, pending_nwin = 0;
+    cudaEvent_t done = nullptr;
 };
 
 namespace lurk {
@@ -317,79 +395,120 @@ static void point_to_bytes(const XYZZ<Fb> &p, int fmt, uint8_t out[96]) {
     memcpy(out, a.x.v, 32); memcpy(out + 32, a.y.v, 32); memcpy(out + 64, one.v, 32);
 }
 
+// enqueue the whole pipeline on stream s, ending with the async read-back of the window sums
 template <class C>
-static int msm_run(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, uint8_t out[96], cudaStream_t s) {
+static int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cudaStream_t s) {
     using Fb = typename C::Base;
     using Fs = typename C::Scalar;
     using Pt = XYZZ<Fb>;
-    if (n == 0) { memset(out, 0, 96); return LURK_OK; }
+    if (ctx->pending) { set_error("a launch is already pending on this context (call lurk_msm_ctx_finish)"); return LURK_ERR_ARG; }
+    if (!ctx->done) LURK_CUDA_TRY(cudaEventCreateWithFlags(&ctx->done, cudaEventDisableTiming));
+    ctx->pending_fmt = fmt;
+    ctx->pending_nwin = 0;
+    if (n == 0) { ctx->pending = true; return LURK_OK; }
     MsmPlan P = make_plan(n, Fs::Params::NBITS);
     MsmScratch &S = ctx->scratch;
+    const uint32_t TB = P.total_buckets;
+    const uint32_t ntiles = (TB + SCAN_TILE - 1) / SCAN_TILE;
     {
         // scratch grows monotonically; a context is normally run at one size (the circuit's witness length)
         auto ensure = [](DevBuf &b, size_t bytes) { return b.bytes >= bytes ? LURK_OK : b.alloc(bytes); };
-        LURK_TRY(ensure(S.counts, ((size_t)P.total_buckets + 1) * 2 * sizeof(uint32_t)));   // counts | cursor
-        LURK_TRY(ensure(S.offsets, ((size_t)P.total_buckets + 1) * sizeof(uint32_t)));
+        LURK_TRY(ensure(S.counts, ((size_t)TB + 1) * 2 * sizeof(uint32_t)));   // counts | cursor
+        LURK_TRY(ensure(S.offsets, ((size_t)TB + 1) * sizeof(uint32_t)));
+        LURK_TRY(ensure(S.tiles, ((size_t)ntiles + 1) * 2 * sizeof(uint32_t)));  // tile sums | tile offsets
         LURK_TRY(ensure(S.sorted, n * (size_t)P.nwin * sizeof(uint32_t)));
-        LURK_TRY(ensure(S.buckets, (size_t)P.total_buckets * sizeof(Pt)));
+        LURK_TRY(ensure(S.buckets, (size_t)TB * sizeof(Pt)));
         LURK_TRY(ensure(S.pkey[0], (size_t)P.t1 * sizeof(uint32_t)));
         LURK_TRY(ensure(S.ppt[0], (size_t)P.t1 * sizeof(Pt)));
-        size_t t2 = ((size_t)P.t1 + 31) / 32;
+        size_t t2 = ((size_t)P.t1 + 7) / 8;
         LURK_TRY(ensure(S.pkey[1], t2 * sizeof(uint32_t)));
         LURK_TRY(ensure(S.ppt[1], t2 * sizeof(Pt)));
-        LURK_TRY(ensure(S.chunks, (size_t)(P.total_buckets / P.chunk) * sizeof(Pt)));
+        LURK_TRY(ensure(S.chunks, (size_t)(TB / P.chunk) * sizeof(Pt)));
         LURK_TRY(ensure(S.wins, 64 * sizeof(Pt)));
         if (!S.h_wins) LURK_CUDA_TRY(cudaMallocHost(&S.h_wins, 64 * sizeof(Pt)));
     }
-    const uint32_t TB = P.total_buckets;
+    if (ntiles > 4096) { set_error("bucket table too large for the scan"); return LURK_ERR_ARG; }
     uint32_t *counts = S.counts.as<uint32_t>();
     uint32_t *cursor = counts + (TB + 1);
     uint32_t *offsets = S.offsets.as<uint32_t>();
+    uint32_t *tile_sums = S.tiles.as<uint32_t>(), *tile_offsets = tile_sums + (ntiles + 1);
     uint32_t *sorted = S.sorted.as<uint32_t>();
     Pt *buckets = S.buckets.as<Pt>();
 
     LURK_CUDA_TRY(cudaMemsetAsync(counts, 0, ((size_t)TB + 1) * 2 * sizeof(uint32_t), s));
     LURK_CUDA_TRY(cudaMemsetAsync(buckets, 0, (size_t)TB * sizeof(Pt), s));   // all-zero = identity
     const unsigned gs = (unsigned)((n + 255) / 256);
+    unsigned launches = 0;
     msm_count_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, P.nb, counts);
-    msm_scan_kernel<<<1, 1024, 0, s>>>(counts, TB, offsets);
+    msm_scan_tile_sums_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_sums);
+    msm_scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_sums, ntiles, tile_offsets);
+    msm_scan_apply_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_offsets, ntiles, offsets);
     msm_scatter_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, P.nb, offsets, cursor, sorted);
     if (ctx->profile) cudaEventRecord(ctx->ev0, s);
     msm_accumulate_kernel<Fb><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, (const Affine<Fb> *)ctx->d_bases, buckets,
                                                                 S.pkey[0].as<uint32_t>(), S.ppt[0].as<Pt>(), P.seg, P.t1);
     if (ctx->profile) cudaEventRecord(ctx->ev1, s);
-    unsigned launches = 4;
-    // shrinking passes over the partial list
+    launches += 6;
+    // shrinking passes over the partial list: one throughput-shaped pass (8 entries per thread), then warp-cooperative
+    // passes (32x per pass, 5 dependent additions each) until a single warp finishes
     uint32_t count = P.t1;
     int cur = 0;
-    for (;;) {
-        const uint32_t seg2 = 32;
-        const uint32_t threads = (count + seg2 - 1) / seg2;
-        const int last = threads == 1;
+    if (count > 32) {
+        const uint32_t seg2 = 8, threads = (count + seg2 - 1) / seg2;
         msm_partial_kernel<Fb><<<(threads + 127) / 128, 128, 0, s>>>(S.pkey[cur].as<uint32_t>(), S.ppt[cur].as<Pt>(), count, buckets,
-                                                                    S.pkey[cur ^ 1].as<uint32_t>(), S.ppt[cur ^ 1].as<Pt>(), seg2, last);
+                                                                    S.pkey[cur ^ 1].as<uint32_t>(), S.ppt[cur ^ 1].as<Pt>(), seg2, 0);
         launches++;
-        if (last) break;
         count = threads;
         cur ^= 1;
     }
-    ctx->last_launches = launches + 2;
+    for (;;) {
+        const uint32_t warps = (count + 31) / 32;
+        const int last = warps == 1;
+        msm_partial_warp_kernel<Fb><<<(warps * 32 + 127) / 128, 128, 0, s>>>(S.pkey[cur].as<uint32_t>(), S.ppt[cur].as<Pt>(), count, buckets,
+                                                                            S.pkey[cur ^ 1].as<uint32_t>(), S.ppt[cur ^ 1].as<Pt>(), last);
+        launches++;
+        if (last) break;
+        count = warps;
+        cur ^= 1;
+    }
     const uint32_t nchunks = TB / P.chunk;
     msm_bucket_reduce_kernel<Fb><<<(nchunks + 127) / 128, 128, 0, s>>>(buckets, P.nb, P.chunk, nchunks, S.chunks.as<Pt>());
     msm_window_sum_kernel<Fb><<<P.nwin, 256, 0, s>>>(S.chunks.as<Pt>(), P.nb / P.chunk, S.wins.as<Pt>());
+    launches += 2;
+    ctx->last_launches = launches;
     LURK_CUDA_TRY(cudaGetLastError());
     LURK_CUDA_TRY(cudaMemcpyAsync(S.h_wins, S.wins.p, (size_t)P.nwin * sizeof(Pt), cudaMemcpyDeviceToHost, s));
-    LURK_CUDA_TRY(cudaStreamSynchronize(s));
+    LURK_CUDA_TRY(cudaEventRecord(ctx->done, s));
+    ctx->pending = true;
+    ctx->pending_c = P.c;
+    ctx->pending_nwin = P.nwin;
+    return LURK_OK;
+}
+
+// wait for the read-back, Horner over the windows on the host, one inversion to affine
+template <class C>
+static int msm_finish(lurk_msm_ctx *ctx, uint8_t out[96]) {
+    using Fb = typename C::Base;
+    using Pt = XYZZ<Fb>;
+    if (!ctx->pending) { set_error("no launch pending on this context"); return LURK_ERR_ARG; }
+    ctx->pending = false;
+    if (ctx->pending_nwin == 0) { memset(out, 0, 96); return LURK_OK; }
+    LURK_CUDA_TRY(cudaEventSynchronize(ctx->done));
     if (ctx->profile) cudaEventElapsedTime(&ctx->last_accumulate_ms, ctx->ev0, ctx->ev1);
-    // Horner over the windows on the host
-    const Pt *w = reinterpret_cast<const Pt *>(S.h_wins);
+    const Pt *w = reinterpret_cast<const Pt *>(ctx->scratch.h_wins);
     Pt acc = Pt::identity();
-    for (int i = P.nwin - 1; i >= 0; i--) {
-        for (int d = 0; d < P.c; d++) acc = acc.dbl();
+    for (int i = ctx->pending_nwin - 1; i >= 0; i--) {
+        for (int d = 0; d < ctx->pending_c; d++) acc = acc.dbl();
         acc.add(w[i]);
     }
-    point_to_bytes(acc, fmt, out);
+    point_to_bytes(acc, ctx->pending_fmt, out);
     return LURK_OK;
+}
+
+template <class C>
+static int msm_run(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, uint8_t out[96], cudaStream_t s) {
+    LURK_TRY(msm_launch<C>(ctx, d_scalars, n, fmt, s));
+    return msm_finish<C>(ctx, out);
 }
 
 template <class C>
@@ -458,6 +577,7 @@ int lurk_msm_ctx_last_profile(lurk_msm_ctx *ctx, float *accumulate_ms, unsigned 
 void lurk_msm_ctx_destroy(lurk_msm_ctx *ctx) {
     if (!ctx) return;
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+    if (ctx->done) cudaEventDestroy(ctx->done);
     if (ctx->owns_bases && ctx->d_bases) cudaFree(ctx->d_bases);
     delete ctx;
 }
@@ -468,6 +588,30 @@ int lurk_msm_ctx_run_dev(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int
     if (n > ctx->n) { set_error("%zu scalars for a commitment key of %zu bases", n, ctx->n); return LURK_ERR_ARG; }
     std::lock_guard<std::mutex> g(ctx->mu);
     return dispatch_curve(ctx->curve_id, [&](auto c) { return msm_run<decltype(c)>(ctx, d_scalars, n, fmt, out_xyz, (cudaStream_t)stream); });
+}
+
+int lurk_msm_ctx_launch_dev(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, void *stream) {
+    if (!ctx) { set_error("null argument"); return LURK_ERR_ARG; }
+    if (fmt != LURK_FMT_CANONICAL && fmt != LURK_FMT_MONTGOMERY) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
+    if (n > ctx->n) { set_error("%zu scalars for a commitment key of %zu bases", n, ctx->n); return LURK_ERR_ARG; }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    return dispatch_curve(ctx->curve_id, [&](auto c) { return msm_launch<decltype(c)>(ctx, d_scalars, n, fmt, (cudaStream_t)stream); });
+}
+int lurk_msm_ctx_finish(lurk_msm_ctx *ctx, uint8_t out_xyz[96]) {
+    if (!ctx || !out_xyz) { set_error("null argument"); return LURK_ERR_ARG; }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    return dispatch_curve(ctx->curve_id, [&](auto c) { return msm_finish<decltype(c)>(ctx, out_xyz); });
+}
+int lurk_msm_ctx_clone(lurk_msm_ctx *ctx, lurk_msm_ctx **out) {
+    if (!ctx || !out) { set_error("null argument"); return LURK_ERR_ARG; }
+    lurk_msm_ctx *c = new lurk_msm_ctx();
+    c->curve_id = ctx->curve_id;
+    c->device = ctx->device;
+    c->n = ctx->n;
+    c->d_bases = ctx->d_bases;     // shared, not owned: the parent must outlive its clones
+    c->owns_bases = false;
+    *out = c;
+    return LURK_OK;
 }
 
 int lurk_msm_ctx_run(lurk_msm_ctx *ctx, const uint8_t *scalars, size_t n, int fmt, uint8_t out_xyz[96]) {

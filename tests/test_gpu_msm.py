@@ -97,3 +97,28 @@ def test_msm_linearity_2_20(L, oracle, spec):
     assert np.array_equal(L.point_sum(curve, np.concatenate([ca, cb])), cab)
     m = 1 << 14
     assert np.array_equal(ck.commit(a[:32 * m]), oracle.msm(curve, bases[:64 * m], a[:32 * m], nthreads=8))
+
+
+def test_msm_async_launch_finish_and_clone(L, oracle, spec):
+    """launch/finish split: two commitments on the same resident key in flight at once (commit(W) and commit(T) of a fold)"""
+    import torch
+    curve, n = 0, 50_000
+    bases = oracle.gen_bases(curve, n)
+    a = scalars_for(spec, curve, n, seed=71, shape="witness")
+    b = scalars_for(spec, curve, n - 1234, seed=72, shape="uniform")
+    ck = L.CommitmentKey(curve, bases)
+    ck2 = ck.clone()
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    ck.launch_device(da.data_ptr(), n, fmt=L.FMT_CANONICAL, stream=s1.cuda_stream)
+    ck2.launch_device(db.data_ptr(), n - 1234, fmt=L.FMT_CANONICAL, stream=s2.cuda_stream)
+    with pytest.raises(L.LurkError):
+        ck.launch_device(da.data_ptr(), n, fmt=L.FMT_CANONICAL, stream=s1.cuda_stream)     # one launch pending per context
+    rb, ra = ck2.finish(), ck.finish()
+    assert np.array_equal(ra, oracle.msm(curve, bases, a, nthreads=8))
+    assert np.array_equal(rb, oracle.msm(curve, bases[:64 * (n - 1234)], b, nthreads=8))
+    with pytest.raises(L.LurkError):
+        ck.finish()                                                                         # nothing pending
+    ms, launches = ck.last_profile()
+    assert launches >= 10
