@@ -14,6 +14,16 @@ struct Affine {
     LURK_HD bool is_identity() const { return x.is_zero() && y.is_zero(); }
 };
 
+// a*b - c*d with one Montgomery reduction (lazy 512-bit accumulation): 200 instead of 272 IMAD.WIDE
+template <class F>
+LURK_HD F mul_sub_mul(const F &a, const F &b, const F &c, const F &d) {
+    WideAcc<typename F::Params> acc;
+    acc.clear();
+    acc.mul_acc(a, b);
+    acc.mul_acc(c.neg(), d);
+    return acc.reduce();
+}
+
 template <class F>
 struct XYZZ {
     F x, y, zz, zzz;
@@ -37,7 +47,7 @@ struct XYZZ {
         F m = xx.dbl() + xx;
         XYZZ r;
         r.x = m.sqr() - s.dbl();
-        r.y = m * (s - r.x) - w * p.y;
+        r.y = mul_sub_mul(m, s - r.x, w, p.y);
         r.zz = v;
         r.zzz = w;
         return r;
@@ -53,7 +63,7 @@ struct XYZZ {
         F m = xx.dbl() + xx;
         XYZZ r;
         r.x = m.sqr() - s.dbl();
-        r.y = m * (s - r.x) - w * y;
+        r.y = mul_sub_mul(m, s - r.x, w, y);
         r.zz = v * zz;
         r.zzz = w * zzz;
         return r;
@@ -76,7 +86,7 @@ struct XYZZ {
         F ppp = p * pp;
         F q_ = x * pp;
         F x3 = r.sqr() - ppp - q_.dbl();
-        y = r * (q_ - x3) - y * ppp;
+        y = mul_sub_mul(r, q_ - x3, y, ppp);
         x = x3;
         zz = zz * pp;
         zzz = zzz * ppp;
@@ -99,7 +109,7 @@ struct XYZZ {
         F ppp = p * pp;
         F q_ = u1 * pp;
         F x3 = r.sqr() - ppp - q_.dbl();
-        y = r * (q_ - x3) - s1 * ppp;
+        y = mul_sub_mul(r, q_ - x3, s1, ppp);
         x = x3;
         zz = zz * o.zz * pp;
         zzz = zzz * o.zzz * ppp;
