@@ -148,25 +148,33 @@ class FoldStepGPU:
         offs += nbd * self.bd_block
         self.slot_region = offs                       # 7808 * rc elements
         assert self.slot_region == RC * 7808
-        # ---- witness vectors (Montgomery, device resident): W2 = [slot witnesses | LEM glue], running W1, E1
+        # ---- witness vectors (Montgomery, device resident).  z = (W, u, X0, X1); W1 / W2 are views into z1 / z2 so the
+        # SpMVs read them in place.  The fresh-instance side (W2, Az2..Cz2) is double buffered: slot witnesses and
+        # commit(W) of step i+1 are chain independent and run ahead of the fold of step i, as the
+        # reference's witness thread does (src/proof/nova.rs:297-326).
         glue = self.nW - self.slot_region
         self.glue_host = torch.from_numpy(rand_elements(rng, glue, "witness")).pin_memory()
-        self.W2 = torch.empty(self.nW * 32, dtype=torch.uint8, device="cuda")
-        self.W1 = dev(rand_elements(rng, self.nW))
+        self.ncols = self.nW + 3
+        tail = dev(rand_elements(rng, 3))
+        self.z1 = torch.empty(self.ncols * 32, dtype=torch.uint8, device="cuda")
+        self.z1[:self.nW * 32] = dev(rand_elements(rng, self.nW))
+        self.z1[self.nW * 32:] = tail
+        self.W1 = self.z1[:self.nW * 32]
+        self.z2, self.W2 = [], []
+        for _ in range(2):
+            z = torch.empty(self.ncols * 32, dtype=torch.uint8, device="cuda")
+            z[self.slot_region * 32:self.nW * 32] = self.glue_host.cuda()
+            z[self.nW * 32:] = tail
+            self.z2.append(z)
+            self.W2.append(z[:self.nW * 32])
         self.E1 = dev(rand_elements(rng, self.nT))
         self.T = torch.empty(self.nT * 32, dtype=torch.uint8, device="cuda")
-        self.W2[self.slot_region * 32:] = self.glue_host.cuda()
-        self.ncols = self.nW + 3                      # z = (W, u, X0, X1)
-        self.z1 = torch.empty(self.ncols * 32, dtype=torch.uint8, device="cuda")
-        self.z2 = torch.empty(self.ncols * 32, dtype=torch.uint8, device="cuda")
-        tail = dev(rand_elements(rng, 3))
-        self.z1[self.nW * 32:] = tail
-        self.z2[self.nW * 32:] = tail
         self.mats = []
         for mean in (2.0, 2.0, 1.5):
             rp, col, val = synthetic_r1cs(rng, self.nT, self.ncols, mean)
             self.mats.append((dev(rp), dev(col), dev(val), int(rp[-1])))
-        self.mv = [torch.empty(self.nT * 32, dtype=torch.uint8, device="cuda") for _ in range(6)]
+        self.mv1 = [torch.empty(self.nT * 32, dtype=torch.uint8, device="cuda") for _ in range(3)]
+        self.mv2 = [[torch.empty(self.nT * 32, dtype=torch.uint8, device="cuda") for _ in range(3)] for _ in range(2)]
         self.u1 = rand_elements(rng, 1)
         self.u2 = rand_elements(rng, 1)
         self.W_sec = dev(rand_elements(rng, SECONDARY_N, "witness"))
@@ -177,78 +185,86 @@ class FoldStepGPU:
         self.d2h_bytes = 0
         torch.cuda.synchronize()
 
-    def stage_inputs(self):
-        """host -> device copy of this step's inputs from pinned memory (the e2e leg)"""
-        if getattr(self, "ev_fold", None) is not None:
-            self.torch.cuda.current_stream().wait_event(self.ev_fold)   # W2's glue region is still read by the last fold
-        for arity, t in self.slot_pre_host.items():
-            self.slot_pre_dev[arity].copy_(t, non_blocking=True)
+    def _setup_streams(self):
+        t = self.torch
+        self.sK = [t.cuda.Stream() for _ in range(3)]      # slot-witness kernels (one stream per arity), commit(W)
+        self.sA = t.cuda.Stream()                          # Az2, Bz2, Cz2 of the prefetched step
+        self.sB = t.cuda.Stream()                          # Az1.., cross term, commit(T), fold
+        self.sS = t.cuda.Stream()                          # secondary-circuit commitments
+        self.ckW = [self.ck, self.ck.clone()]
+        self.ckW[1].set_profiling(True)
+        self.ckT = self.ck.clone()
+        self.ckT.set_profiling(True)
+        self.ck2b = self.ck2.clone()
+        self.ev_fold = [None, None]                        # fold that last read W2[b]
+        self.ev_A = [None, None]                           # stage A of buffer b complete (Az2.. ready)
+        self.prefetched = None                             # step index whose stage A is in flight
+        self.step_index = 0
+        self.k_A = 0
+
+    def stage_inputs(self, b):
+        """host -> device copy of one step's inputs from pinned memory (the e2e leg), into buffer b"""
+        t = self.torch
+        cur = t.cuda.current_stream()
+        if self.ev_fold[b] is not None:
+            cur.wait_event(self.ev_fold[b])                # W2[b]'s glue region is still read by an earlier fold
+        for arity, h in self.slot_pre_host.items():
+            self.slot_pre_dev[arity].copy_(h, non_blocking=True)
         self.bd_dev.copy_(self.bd_host, non_blocking=True)
-        self.W2[self.slot_region * 32:].copy_(self.glue_host, non_blocking=True)
+        self.W2[b][self.slot_region * 32:].copy_(self.glue_host, non_blocking=True)
 
-    def _streams(self):
-        if not hasattr(self, "sK"):
-            t = self.torch
-            self.sK = [t.cuda.Stream() for _ in range(3)]      # slot-witness kernels, one stream per arity
-            self.sB = t.cuda.Stream()                          # SpMV / cross term / commit(T) / fold
-            self.sS = t.cuda.Stream()                          # secondary-circuit commitments
-            self.ckT = self.ck.clone()
-            self.ckT.set_profiling(True)
-            self.ck2b = self.ck2.clone()
-            self.ev_fold = None
-        return self.sK, self.sB, self.sS
-
-    def step(self, group=None):
-        """One fold.  Independent pieces run on separate streams so the latency-bound tails of one commitment
-        (partial passes, bucket reduce, read-back) overlap the multiply-bound kernels of the other."""
+    def stage_A(self, b, staged):
+        """chain-independent half of a step: slot witnesses -> W2[b], commit(W2[b]) enqueued, Az2/Bz2/Cz2"""
         L, lib, chk, t = self.L, self.lib, self.L._capi.check, self.torch
         M = L.FMT_MONTGOMERY
-        sK, sB, sS = self._streams()
-        k = 0
+        if staged:
+            self.stage_inputs(b)
         cur = t.cuda.current_stream()
-        for st in (*sK, sB, sS):
-            st.wait_stream(cur)                                # inputs staged on the current stream
-        if self.ev_fold is not None:
-            for st in sK:
-                st.wait_event(self.ev_fold)                    # W2 is read by the previous step's fold
-        # K3: slot witnesses straight into W2 (Montgomery in, Montgomery out), one stream per slot type
+        k = 0
+        for st in (*self.sK, self.sA):
+            st.wait_stream(cur)
+            if self.ev_fold[b] is not None:
+                st.wait_event(self.ev_fold[b])
+        W2 = self.W2[b]
         evs = []
-        for (arity, n, off, blk), st in zip(self.slot_layout, sK):
+        for (arity, n, off, blk), st in zip(self.slot_layout, self.sK):
             chk(lib.lurk_poseidon_witness_batch_dev(FIELD, arity, self.slot_pre_dev[arity].data_ptr(), n,
-                                                    self.W2.data_ptr() + off * 32, M, C.c_void_p(st.cuda_stream))); k += 1
-        chk(lib.lurk_bitdecomp_witness_batch_dev(FIELD, self.bd_dev.data_ptr(), self.bd_n, self.W2.data_ptr() + self.bd_off * 32, M,
-                                                 C.c_void_p(sK[2].cuda_stream))); k += 1
-        for st in sK:
+                                                    W2.data_ptr() + off * 32, M, C.c_void_p(st.cuda_stream))); k += 1
+        chk(lib.lurk_bitdecomp_witness_batch_dev(FIELD, self.bd_dev.data_ptr(), self.bd_n, W2.data_ptr() + self.bd_off * 32, M,
+                                                 C.c_void_p(self.sK[2].cuda_stream))); k += 1
+        for st in self.sK:
             e = t.cuda.Event(); e.record(st); evs.append(e)
-        # K4: comm_W (partial over this rank's key shard) -- enqueue only
-        sK[0].wait_event(evs[1]); sK[0].wait_event(evs[2])
-        self.ck.launch_device(self.W2.data_ptr(), self.nW, fmt=M, stream=sK[0].cuda_stream)
-        # K5 on sB: Az1,Bz1,Cz1 need only the running instance; Az2.. wait for the slot witnesses
-        nb = self.nW * 32
+        self.sK[0].wait_event(evs[1]); self.sK[0].wait_event(evs[2])
+        self.ckW[b].launch_device(W2.data_ptr(), self.nW, fmt=M, stream=self.sK[0].cuda_stream)
+        sa = C.c_void_p(self.sA.cuda_stream)
+        for e in evs:
+            self.sA.wait_event(e)
+        for i, (rp, col, val, _nnz) in enumerate(self.mats):
+            chk(lib.lurk_spmv_csr_dev(FIELD, rp.data_ptr(), col.data_ptr(), val.data_ptr(), self.nT, self.z2[b].data_ptr(),
+                                      self.mv2[b][i].data_ptr(), sa)); k += 1
+        self.ev_A[b] = t.cuda.Event(); self.ev_A[b].record(self.sA)
+        self.k_A = k
+
+    def stage_B(self, b, group=None):
+        """chain-dependent half: Az1.., cross term, commit(T), challenge, fold"""
+        L, lib, chk, t = self.L, self.lib, self.L._capi.check, self.torch
+        M = L.FMT_MONTGOMERY
+        sB, sS = self.sB, self.sS
         sb = C.c_void_p(sB.cuda_stream)
-        with t.cuda.stream(sB):
-            self.z1[:nb].copy_(self.W1, non_blocking=True)
+        k = 0
         for i, (rp, col, val, _nnz) in enumerate(self.mats):
             chk(lib.lurk_spmv_csr_dev(FIELD, rp.data_ptr(), col.data_ptr(), val.data_ptr(), self.nT, self.z1.data_ptr(),
-                                      self.mv[2 * i].data_ptr(), sb)); k += 1
-        for e in evs:
-            sB.wait_event(e)
-        with t.cuda.stream(sB):
-            self.z2[:nb].copy_(self.W2, non_blocking=True)
-        for i, (rp, col, val, _nnz) in enumerate(self.mats):
-            chk(lib.lurk_spmv_csr_dev(FIELD, rp.data_ptr(), col.data_ptr(), val.data_ptr(), self.nT, self.z2.data_ptr(),
-                                      self.mv[2 * i + 1].data_ptr(), sb)); k += 1
-        az1, az2, bz1, bz2, cz1, cz2 = self.mv
+                                      self.mv1[i].data_ptr(), sb)); k += 1
+        sB.wait_event(self.ev_A[b])
+        az1, bz1, cz1 = self.mv1
+        az2, bz2, cz2 = self.mv2[b]
         chk(lib.lurk_cross_term_dev(FIELD, az1.data_ptr(), bz1.data_ptr(), cz1.data_ptr(), az2.data_ptr(), bz2.data_ptr(), cz2.data_ptr(),
                                     L._capi.np_ptr(self.u1), L._capi.np_ptr(self.u2), self.nT, self.T.data_ptr(), sb)); k += 1
-        # K4: comm_T
         self.ckT.launch_device(self.T.data_ptr(), self.nT, fmt=M, stream=sB.cuda_stream)
-        # secondary circuit (Grumpkin): two small commitments
         self.ck2.launch_device(self.W_sec.data_ptr(), SECONDARY_N, fmt=M, stream=sS.cuda_stream)
         self.ck2b.launch_device(self.T_sec.data_ptr(), SECONDARY_N, fmt=M, stream=sS.cuda_stream)
-        # collect
-        cw = self.ck.finish()
-        ms, kl = self.ck.last_profile(); self.acc_ms.append(ms); k += kl
+        cw = self.ckW[b].finish()
+        ms, kl = self.ckW[b].last_profile(); self.acc_ms.append(ms); k += kl
         ct = self.ckT.finish()
         ms, kl = self.ckT.last_profile(); self.acc_ms.append(ms); k += kl
         # exchange: the two partial commitments (all-gather + local adds; nothing to do on one GPU)
@@ -263,16 +279,36 @@ class FoldStepGPU:
         # challenge r (stand-in for the Poseidon-sponge RO on the CPU: 128 bits derived from the commitments)
         r = np.zeros(32, dtype=np.uint8)
         r[:16] = np.frombuffer(hashlib.sha256(cw.tobytes() + ct.tobytes()).digest()[:16], dtype=np.uint8)
-        # K5: fold (on sB, after commit(T); W2 is free again once this is done)
-        chk(lib.lurk_axpy_dev(FIELD, self.W1.data_ptr(), self.W2.data_ptr(), L._capi.np_ptr(r), self.nW, self.W1.data_ptr(), sb)); k += 1
+        chk(lib.lurk_axpy_dev(FIELD, self.W1.data_ptr(), self.W2[b].data_ptr(), L._capi.np_ptr(r), self.nW, self.W1.data_ptr(), sb)); k += 1
         chk(lib.lurk_axpy_dev(FIELD, self.E1.data_ptr(), self.T.data_ptr(), L._capi.np_ptr(r), self.nT, self.E1.data_ptr(), sb)); k += 1
-        self.ev_fold = t.cuda.Event(); self.ev_fold.record(sB)
+        self.ev_fold[b] = t.cuda.Event(); self.ev_fold[b].record(sB)
         self.ck2.finish(); k += self.ck2.last_profile()[1]
         self.ck2b.finish(); k += self.ck2b.last_profile()[1]
-        cur.wait_stream(sB)                                    # the step ends when the fold is enqueued behind it
-        self.launches = k
+        return cw, ct, k
+
+    def step(self, staged=False, group=None):
+        """One fold.  Stage A of the next step is enqueued before this step's commitments are collected, so its
+        slot witnesses / commit(W) fill the GPU while the host finishes this fold."""
+        if not hasattr(self, "sK"):
+            self._setup_streams()
+        i = self.step_index
+        b = i & 1
+        if self.prefetched != i:
+            self.stage_A(b, staged)
+        kA = self.k_A
+        self.stage_A(b ^ 1, staged)                       # prefetch step i+1
+        self.prefetched = i + 1
+        cw, ct, kB = self.stage_B(b, group)
+        self.step_index = i + 1
+        self.launches = kA + kB
         self.d2h_bytes = 2 * 96 + 4 * 16 * 128        # result points + window sums read back by the 4 commitments
         return cw, ct
+
+    def drain(self):
+        """collect the commit(W) of a prefetched step that will not be folded (end of a timed region)"""
+        if getattr(self, "prefetched", None) is not None and self.prefetched == self.step_index:
+            self.ckW[self.step_index & 1].finish()
+            self.prefetched = None
 
 
 def run_gpu(args):
@@ -309,6 +345,7 @@ def run_gpu(args):
         e0.record()
         for _ in range(steps):
             fn()
+        wl.drain()                        # the prefetched half-step is inside the timed region (it is extra work)
         torch.cuda.synchronize()          # work runs on several streams: close the region after all of them drained
         e1.record()
         barrier()
@@ -318,11 +355,10 @@ def run_gpu(args):
         return float(ms.item())
 
     def step_resident():
-        wl.step()
+        wl.step(staged=False)
 
     def step_e2e():
-        wl.stage_inputs()
-        wl.step()
+        wl.step(staged=True)
 
     for _ in range(max(args.warmup, 3)):
         step_e2e()

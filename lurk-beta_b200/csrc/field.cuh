@@ -311,7 +311,9 @@ struct WideAcc {
         row<4>(a.v, b.v[4]); row<5>(a.v, b.v[5]); row<6>(a.v, b.v[6]); row<7>(a.v, b.v[7]);
     }
 
-    // requires sum < 9 p^2
+    // k accumulated products give a value < (k p / 2^256 + 1) p before the final conditional subtractions:
+    // ROUNDS = 3 is enough for k <= 11 (Pasta, p/2^256 = 0.25) or k <= 15 (BN254, 0.19); use ROUNDS = 4 up to k = 15.
+    template <int ROUNDS = 3>
     LURK_HD Fe<P> reduce() {
         // fold the pending carries
         e[8] = cc::add_cc(e[8], ce[0]);   e[9] = cc::addc_cc(e[9], 0);
@@ -346,9 +348,9 @@ struct WideAcc {
 #pragma unroll
         for (int k = 1; k < 8; k++) t[8 + k] = cc::addc_cc(t[8 + k], r[k]);
         t[16] = cc::addc(t[16], r[8]);
-        // value = t[8..16] < 3.25 p: three conditional subtractions over 9 words
+        // value = t[8..16] < (ROUNDS + 1) p: conditional subtractions over 9 words
 #pragma unroll
-        for (int round = 0; round < 3; round++) {
+        for (int round = 0; round < ROUNDS; round++) {
             uint32_t d[9];
             d[0] = cc::sub_cc(t[8], P::MOD(0));
 #pragma unroll

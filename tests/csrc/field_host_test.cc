@@ -43,11 +43,11 @@ static int run_dot(int k, const uint8_t *a, const uint8_t *b, uint8_t *out) {
         memcpy(x.v, a + 32 * i, 32); memcpy(y.v, b + 32 * i, 32);
         acc.mul_acc(F::from_canonical(x), F::from_canonical(y));
     }
-    F r = acc.reduce().to_canonical();
+    F r = (k > 11 ? acc.template reduce<4>() : acc.reduce()).to_canonical();
     memcpy(out, r.v, 32);
     return 0;
 }
-// Montgomery-form dot product of k <= 9 pairs through the lazy accumulator
+// Montgomery-form dot product of k <= 15 pairs through the lazy accumulator
 extern "C" int fe_test_dot(int field, int k, const uint8_t *a, const uint8_t *b, uint8_t *out) {
     switch (field) {
         case 0: return run_dot<Fe<Bn254Fr>>(k, a, b, out);

@@ -101,8 +101,8 @@ def test_limb_arithmetic_against_bigints(fieldlib, spec, field):
         assert int.from_bytes(out.raw, "little") == pow(a, p - 2, p)
     # lazy dot products (one reduction per MDS row)
     for trial in range(300):
-        k = rnd.randint(1, 9)
-        A = [p - 1] * k if trial < 5 else [rnd.randrange(p) for _ in range(k)]
-        B = [p - 1] * k if trial < 5 else [rnd.randrange(p) for _ in range(k)]
+        k = rnd.randint(1, 15)
+        A = [p - 1] * k if trial < 30 else [rnd.randrange(p) for _ in range(k)]
+        B = [p - 1] * k if trial < 30 else [rnd.randrange(p) for _ in range(k)]
         fieldlib.fe_test_dot(field, k, b"".join(x.to_bytes(32, "little") for x in A), b"".join(x.to_bytes(32, "little") for x in B), out)
         assert int.from_bytes(out.raw, "little") == sum(x * y for x, y in zip(A, B)) % p
