@@ -49,6 +49,7 @@ PROTOTYPES = {
     "lurk_msm_ctx_launch_dev": (_i, [_vp, _vp, _sz, _i, _vp]),
     "lurk_msm_ctx_finish": (_i, [_vp, _vp]),
     "lurk_msm_ctx_clone": (_i, [_vp, C.POINTER(_vp)]),
+    "lurk_msm_ctx_precompute": (_i, [_vp]),
     "lurk_msm_ctx_set_profiling": (_i, [_vp, _i]),
     "lurk_msm_ctx_last_profile": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint)]),
     "lurk_point_sum": (_i, [_i, _vp, _sz, _i, _vp]),

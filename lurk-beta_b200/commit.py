@@ -55,6 +55,11 @@ class CommitmentKey:
         _capi.check(_capi.lib().lurk_msm_ctx_finish(self._ctx, _capi.np_ptr(out)))
         return out
 
+    def precompute(self):
+        """build the fixed-base window table on the device (once per key; call before clone())"""
+        _capi.check(_capi.lib().lurk_msm_ctx_precompute(self._ctx))
+        return self
+
     def clone(self):
         """another context on the same device-resident key (own scratch), for overlapping commitments"""
         other = CommitmentKey.__new__(CommitmentKey)

@@ -224,6 +224,8 @@ struct alignas(16) Fe {
         return r;
     }
 #endif
+    // A dedicated squaring (36 word products + doubling instead of 64) was measured SLOWER on B200: the extra
+    // carry/shift work lands on the ALU pipe and as IMAD.MOV on the FMA pipe (round-1 notes in DESIGN.md).
     LURK_HD Fe sqr() const { return *this * *this; }
     LURK_HD Fe pow5() const { Fe x2 = sqr(); Fe x4 = x2.sqr(); return x4 * *this; }
 
@@ -265,6 +267,44 @@ struct alignas(16) Fe {
         return pow_raw(e);
     }
 };
+
+// ----------------------------------------------------------------------------- wide reduction
+// Word-serial Montgomery reduction of a 17-word value t (t[16] small): returns t / 2^256 mod p, fully reduced.
+// Row carries that leave an 8-word window go to r[] (columns 8..16): they never feed a reduction multiplier.
+// The value before the conditional subtractions must be < (ROUNDS + 1) p.
+template <class P, int ROUNDS>
+LURK_HD Fe<P> redc17(uint32_t *t) {
+    uint32_t r[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) r[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t mi = t[i] * P::M0;
+        Fe<P>::template cmad_mod<0>(t + i, mi);
+        r[i] = cc::addc(r[i], 0);
+        Fe<P>::template cmad_mod<1>(t + i + 1, mi);
+        r[i + 1] = cc::addc(r[i + 1], 0);
+    }
+    t[8] = cc::add_cc(t[8], r[0]);
+#pragma unroll
+    for (int k = 1; k < 8; k++) t[8 + k] = cc::addc_cc(t[8 + k], r[k]);
+    t[16] = cc::addc(t[16], r[8]);
+#pragma unroll
+    for (int round = 0; round < ROUNDS; round++) {
+        uint32_t d[9];
+        d[0] = cc::sub_cc(t[8], P::MOD(0));
+#pragma unroll
+        for (int k = 1; k < 8; k++) d[k] = cc::subc_cc(t[8 + k], P::MOD(k));
+        d[8] = cc::subc_cc(t[16], 0);
+        uint32_t borrow = cc::subc(0, 0);
+#pragma unroll
+        for (int k = 0; k < 9; k++) t[8 + k] = borrow ? t[8 + k] : d[k];
+    }
+    Fe<P> out;
+#pragma unroll
+    for (int k = 0; k < 8; k++) out.v[k] = t[8 + k];
+    return out;
+}
 
 // ----------------------------------------------------------------------------- lazy dot products
 // Accumulates up to 9 full 256x256-bit products and performs ONE Montgomery reduction at the end:
@@ -332,38 +372,7 @@ struct WideAcc {
 #pragma unroll
         for (int k = 2; k < 16; k++) t[k] = cc::addc_cc(e[k], o[k - 1]);
         t[16] = cc::addc(e[16], o[15]);
-        // word-serial Montgomery reduction; row carries go to r[] (columns 8..16)
-        uint32_t r[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) r[k] = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            uint32_t mi = t[i] * P::M0;
-            Fe<P>::template cmad_mod<0>(t + i, mi);
-            r[i] = cc::addc(r[i], 0);
-            Fe<P>::template cmad_mod<1>(t + i + 1, mi);
-            r[i + 1] = cc::addc(r[i + 1], 0);
-        }
-        t[8] = cc::add_cc(t[8], r[0]);
-#pragma unroll
-        for (int k = 1; k < 8; k++) t[8 + k] = cc::addc_cc(t[8 + k], r[k]);
-        t[16] = cc::addc(t[16], r[8]);
-        // value = t[8..16] < (ROUNDS + 1) p: conditional subtractions over 9 words
-#pragma unroll
-        for (int round = 0; round < ROUNDS; round++) {
-            uint32_t d[9];
-            d[0] = cc::sub_cc(t[8], P::MOD(0));
-#pragma unroll
-            for (int k = 1; k < 8; k++) d[k] = cc::subc_cc(t[8 + k], P::MOD(k));
-            d[8] = cc::subc_cc(t[16], 0);
-            uint32_t borrow = cc::subc(0, 0);
-#pragma unroll
-            for (int k = 0; k < 9; k++) t[8 + k] = borrow ? t[8 + k] : d[k];
-        }
-        Fe<P> out;
-#pragma unroll
-        for (int k = 0; k < 8; k++) out.v[k] = t[8 + k];
-        return out;
+        return redc17<P, ROUNDS>(t);
     }
 };
 

@@ -41,16 +41,35 @@ struct MsmPlan {
     uint32_t seg = 0;      // sorted entries per level-1 thread
     uint32_t t1 = 0;       // level-1 threads = partial slots
     uint32_t chunk = 0;    // buckets per bucket-reduce thread
+    // fixed-base mode (window multiples of every base precomputed): one shared bucket set of 2^(c-1) buckets, cut into
+    // `vwin` virtual windows of `nb` buckets for the reduction; entries address table[w * key_n + i]
+    bool fixed = false;
+    uint32_t vwin = 0;
 };
 
-static MsmPlan make_plan(size_t n, int scalar_bits) {
+static int fixed_base_window(size_t key_n) {
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= key_n) lg++;
+    return std::min(20, std::max(10, lg - 1));
+}
+
+static MsmPlan make_plan(size_t n, int scalar_bits, int fixed_c = 0) {
     MsmPlan p;
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
-    p.c = std::min(20, std::max(4, lg - 5));
+    p.c = fixed_c ? fixed_c : std::min(20, std::max(4, lg - 5));
     p.nwin = scalar_bits / p.c + 1;
-    p.nb = 1u << (p.c - 1);
-    p.total_buckets = p.nb * (uint32_t)p.nwin;
+    if (fixed_c) {
+        p.fixed = true;
+        const uint32_t all = 1u << (p.c - 1);
+        p.nb = std::min<uint32_t>(all, 1u << 15);
+        p.vwin = all / p.nb;
+        p.total_buckets = all;
+    } else {
+        p.nb = 1u << (p.c - 1);
+        p.vwin = (uint32_t)p.nwin;
+        p.total_buckets = p.nb * (uint32_t)p.nwin;
+    }
     size_t cap = n * (size_t)p.nwin;
     size_t want_threads = (size_t)sm_count() * 1024;
     size_t seg = (cap + want_threads - 1) / want_threads;
@@ -72,7 +91,7 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t k[8], int bit, in
 }
 
 template <class Fs>
-__global__ void __launch_bounds__(256) msm_count_kernel(const Fs *__restrict__ scalars, size_t n, int fmt, int c, int nwin, uint32_t nb,
+__global__ void __launch_bounds__(256) msm_count_kernel(const Fs *__restrict__ scalars, size_t n, int fmt, int c, int nwin, uint32_t key_stride,
                                                         uint32_t *__restrict__ counts) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
@@ -87,7 +106,7 @@ __global__ void __launch_bounds__(256) msm_count_kernel(const Fs *__restrict__ s
         uint32_t neg = raw > half;
         uint32_t mag = neg ? (1u << c) - raw : raw;
         carry = neg;
-        uint32_t key = (live && mag) ? (uint32_t)w * nb + (mag - 1) : KEY_NONE;
+        uint32_t key = (live && mag) ? (uint32_t)w * key_stride + (mag - 1) : KEY_NONE;
         uint32_t peers = __match_any_sync(0xffffffffu, key);
         if (key != KEY_NONE && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(counts + key, (uint32_t)__popc(peers));
     }
@@ -150,9 +169,9 @@ __global__ void __launch_bounds__(1024) msm_scan_apply_kernel(const uint32_t *__
 }
 
 template <class Fs>
-__global__ void __launch_bounds__(256) msm_scatter_kernel(const Fs *__restrict__ scalars, size_t n, int fmt, int c, int nwin, uint32_t nb,
-                                                          const uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor,
-                                                          uint32_t *__restrict__ sorted) {
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const Fs *__restrict__ scalars, size_t n, int fmt, int c, int nwin, uint32_t key_stride,
+                                                          uint32_t base_stride, const uint32_t *__restrict__ offsets,
+                                                          uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
     Fs k = Fs::zero();
@@ -165,7 +184,7 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const Fs *__restrict__
         uint32_t neg = raw > half;
         uint32_t mag = neg ? (1u << c) - raw : raw;
         carry = neg;
-        uint32_t key = (live && mag) ? (uint32_t)w * nb + (mag - 1) : KEY_NONE;
+        uint32_t key = (live && mag) ? (uint32_t)w * key_stride + (mag - 1) : KEY_NONE;
         uint32_t peers = __match_any_sync(0xffffffffu, key);
         uint32_t leader = (uint32_t)(__ffs(peers) - 1);
         uint32_t base = 0;
@@ -173,7 +192,7 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const Fs *__restrict__
         base = __shfl_sync(0xffffffffu, base, leader);
         if (key != KEY_NONE) {
             uint32_t rank = __popc(peers & ((1u << lane) - 1));
-            sorted[offsets[key] + base + rank] = (uint32_t)i | (neg << 31);
+            sorted[offsets[key] + base + rank] = ((uint32_t)i + (uint32_t)w * base_stride) | (neg << 31);
         }
     }
 }
@@ -318,7 +337,8 @@ __global__ void __launch_bounds__(128) msm_partial_warp_kernel(const uint32_t *_
 // per chunk of `chunk` buckets [b0, b0+chunk) of window w:  sum_b (b+1) B_b = tri + b0 * S
 template <class Fb>
 __global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(const XYZZ<Fb> *__restrict__ bucket_acc, uint32_t nb, uint32_t chunk,
-                                                                uint32_t nchunks_total, XYZZ<Fb> *__restrict__ chunk_out) {
+                                                                uint32_t nchunks_total, XYZZ<Fb> *__restrict__ chunk_out,
+                                                                XYZZ<Fb> *__restrict__ chunk_sum_out) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nchunks_total) return;
     const uint32_t per_win = nb / chunk;
@@ -332,6 +352,7 @@ __global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(const XYZZ<Fb> *
     }
     if (b0) tri.add(run.mul_u32(b0));
     store_xyzz(chunk_out + g, tri);
+    if (chunk_sum_out) store_xyzz(chunk_sum_out + g, run);   // plain sum of the chunk (fixed-base mode)
 }
 
 // one CTA per window: sum of its chunk results
@@ -350,6 +371,42 @@ __global__ void __launch_bounds__(256) msm_window_sum_kernel(const XYZZ<Fb> *__r
     if (tid == 0) store_xyzz(win_out + w, sm[0]);
 }
 
+// Fixed-base table: table[w * n + i] = 2^(c w) * bases[i], affine.  One thread per base walks the windows with c
+// doublings each (XYZZ), then normalises its nwin points with one inversion (Montgomery's trick on the ZZZ coordinates).
+static constexpr int MSM_MAX_TABLE_WINDOWS = 26;
+template <class Fb>
+__global__ void __launch_bounds__(128) msm_precompute_kernel(const Affine<Fb> *__restrict__ bases, size_t n, int c, int nwin,
+                                                             Affine<Fb> *__restrict__ table) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Affine<Fb> p0 = load_affine(bases + i);
+    XYZZ<Fb> pts[MSM_MAX_TABLE_WINDOWS];
+    Fb pref[MSM_MAX_TABLE_WINDOWS];
+    XYZZ<Fb> cur = XYZZ<Fb>::from_affine(p0);
+    Fb run = Fb::one();
+    for (int w = 0; w < nwin; w++) {
+        if (w) for (int d = 0; d < c; d++) cur = cur.dbl();
+        pts[w] = cur;
+        pref[w] = run;
+        if (!cur.is_identity()) run = run * cur.zzz;
+    }
+    Fb inv = run.inv();
+    for (int w = nwin - 1; w >= 0; w--) {
+        Affine<Fb> a;
+        a.x = Fb::zero();
+        a.y = Fb::zero();
+        if (!pts[w].is_identity()) {
+            const Fb zi = inv * pref[w];            // 1 / ZZZ_w
+            inv = inv * pts[w].zzz;
+            const Fb zz_inv = (zi * pts[w].zz).sqr();
+            a.x = pts[w].x * zz_inv;
+            a.y = pts[w].y * zi;
+        }
+        store_fe(&table[(size_t)w * n + i].x, a.x);
+        store_fe(&table[(size_t)w * n + i].y, a.y);
+    }
+}
+
 // affine bases: canonical -> Montgomery in place
 template <class Fb>
 __global__ void __launch_bounds__(256) msm_bases_to_mont_kernel(Fb *coords, size_t count) {
@@ -359,7 +416,7 @@ __global__ void __launch_bounds__(256) msm_bases_to_mont_kernel(Fb *coords, size
 
 // ----------------------------------------------------------------------------- context
 struct MsmScratch {
-    DevBuf counts, offsets, tiles, sorted, buckets, pkey[2], ppt[2], chunks, wins, scalars;
+    DevBuf counts, offsets, tiles, sorted, buckets, pkey[2], ppt[2], chunks, chunk_sums, wins, scalars;
     void *h_wins = nullptr;   // pinned
     ~MsmScratch() { if (h_wins) cudaFreeHost(h_wins); }
 };
@@ -374,6 +431,9 @@ struct lurk_msm_ctx {
     size_t n = 0;
     void *d_bases = nullptr;
     bool owns_bases = false;
+    void *d_table = nullptr;      // fixed-base table (nwin x n affine), optional
+    bool owns_table = false;
+    int fixed_c = 0;
     std::mutex mu;
     MsmScratch scratch;
     // optional device timing of the dominant kernel (bucket accumulation), on the launching stream
@@ -384,6 +444,8 @@ struct lurk_msm_ctx {
     // launch / finish split
     bool pending = false;
     int pending_fmt = 0, pending_c = 0, pending_nwin = 0;
+    bool pending_fixed = false;
+    uint32_t pending_vwin = 0, pending_nb = 0;
     cudaEvent_t done = nullptr;
 };
 
@@ -410,7 +472,8 @@ static int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fm
     ctx->pending_fmt = fmt;
     ctx->pending_nwin = 0;
     if (n == 0) { ctx->pending = true; return LURK_OK; }
-    MsmPlan P = make_plan(n, Fs::Params::NBITS);
+    const bool fixed = ctx->d_table != nullptr;
+    MsmPlan P = make_plan(n, Fs::Params::NBITS, fixed ? ctx->fixed_c : 0);
     MsmScratch &S = ctx->scratch;
     const uint32_t TB = P.total_buckets;
     const uint32_t ntiles = (TB + SCAN_TILE - 1) / SCAN_TILE;
@@ -428,8 +491,9 @@ static int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fm
         LURK_TRY(ensure(S.pkey[1], t2 * sizeof(uint32_t)));
         LURK_TRY(ensure(S.ppt[1], t2 * sizeof(Pt)));
         LURK_TRY(ensure(S.chunks, (size_t)(TB / P.chunk) * sizeof(Pt)));
-        LURK_TRY(ensure(S.wins, 64 * sizeof(Pt)));
-        if (!S.h_wins) LURK_CUDA_TRY(cudaMallocHost(&S.h_wins, 64 * sizeof(Pt)));
+        if (fixed) LURK_TRY(ensure(S.chunk_sums, (size_t)(TB / P.chunk) * sizeof(Pt)));
+        LURK_TRY(ensure(S.wins, 128 * sizeof(Pt)));
+        if (!S.h_wins) LURK_CUDA_TRY(cudaMallocHost(&S.h_wins, 128 * sizeof(Pt)));
     }
     if (ntiles > 4096) { set_error("bucket table too large for the scan"); return LURK_ERR_ARG; }
     uint32_t *counts = S.counts.as<uint32_t>();
@@ -443,13 +507,16 @@ static int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fm
     LURK_CUDA_TRY(cudaMemsetAsync(buckets, 0, (size_t)TB * sizeof(Pt), s));   // all-zero = identity
     const unsigned gs = (unsigned)((n + 255) / 256);
     unsigned launches = 0;
-    msm_count_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, P.nb, counts);
+    const uint32_t key_stride = fixed ? 0u : P.nb;                 // fixed-base: all windows share one bucket set
+    const uint32_t base_stride = fixed ? (uint32_t)ctx->n : 0u;     // ... and address table[w * n + i]
+    const Affine<Fb> *bases = (const Affine<Fb> *)(fixed ? ctx->d_table : ctx->d_bases);
+    msm_count_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, key_stride, counts);
     msm_scan_tile_sums_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_sums);
     msm_scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_sums, ntiles, tile_offsets);
     msm_scan_apply_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_offsets, ntiles, offsets);
-    msm_scatter_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, P.nb, offsets, cursor, sorted);
+    msm_scatter_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, key_stride, base_stride, offsets, cursor, sorted);
     if (ctx->profile) cudaEventRecord(ctx->ev0, s);
-    msm_accumulate_kernel<Fb><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, (const Affine<Fb> *)ctx->d_bases, buckets,
+    msm_accumulate_kernel<Fb><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, bases, buckets,
                                                                 S.pkey[0].as<uint32_t>(), S.ppt[0].as<Pt>(), P.seg, P.t1);
     if (ctx->profile) cudaEventRecord(ctx->ev1, s);
     launches += 6;
@@ -476,16 +543,21 @@ static int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fm
         cur ^= 1;
     }
     const uint32_t nchunks = TB / P.chunk;
-    msm_bucket_reduce_kernel<Fb><<<(nchunks + 127) / 128, 128, 0, s>>>(buckets, P.nb, P.chunk, nchunks, S.chunks.as<Pt>());
-    msm_window_sum_kernel<Fb><<<P.nwin, 256, 0, s>>>(S.chunks.as<Pt>(), P.nb / P.chunk, S.wins.as<Pt>());
+    msm_bucket_reduce_kernel<Fb><<<(nchunks + 127) / 128, 128, 0, s>>>(buckets, P.nb, P.chunk, nchunks, S.chunks.as<Pt>(),
+                                                                       fixed ? S.chunk_sums.as<Pt>() : nullptr);
+    msm_window_sum_kernel<Fb><<<P.vwin, 256, 0, s>>>(S.chunks.as<Pt>(), P.nb / P.chunk, S.wins.as<Pt>());
     launches += 2;
+    if (fixed) { msm_window_sum_kernel<Fb><<<P.vwin, 256, 0, s>>>(S.chunk_sums.as<Pt>(), P.nb / P.chunk, S.wins.as<Pt>() + 64); launches++; }
     ctx->last_launches = launches;
     LURK_CUDA_TRY(cudaGetLastError());
-    LURK_CUDA_TRY(cudaMemcpyAsync(S.h_wins, S.wins.p, (size_t)P.nwin * sizeof(Pt), cudaMemcpyDeviceToHost, s));
+    LURK_CUDA_TRY(cudaMemcpyAsync(S.h_wins, S.wins.p, (size_t)(fixed ? 128 : P.vwin) * sizeof(Pt), cudaMemcpyDeviceToHost, s));
     LURK_CUDA_TRY(cudaEventRecord(ctx->done, s));
     ctx->pending = true;
     ctx->pending_c = P.c;
     ctx->pending_nwin = P.nwin;
+    ctx->pending_fixed = fixed;
+    ctx->pending_vwin = P.vwin;
+    ctx->pending_nb = P.nb;
     return LURK_OK;
 }
 
@@ -501,9 +573,17 @@ static int msm_finish(lurk_msm_ctx *ctx, uint8_t out[96]) {
     if (ctx->profile) cudaEventElapsedTime(&ctx->last_accumulate_ms, ctx->ev0, ctx->ev1);
     const Pt *w = reinterpret_cast<const Pt *>(ctx->scratch.h_wins);
     Pt acc = Pt::identity();
-    for (int i = ctx->pending_nwin - 1; i >= 0; i--) {
-        for (int d = 0; d < ctx->pending_c; d++) acc = acc.dbl();
-        acc.add(w[i]);
+    if (ctx->pending_fixed) {
+        // shared bucket set cut into virtual windows: sum_v (R_v + (v * nb) * S_v)
+        for (uint32_t v = 0; v < ctx->pending_vwin; v++) {
+            acc.add(w[v]);
+            if (v) acc.add(w[64 + v].mul_u32(v * ctx->pending_nb));
+        }
+    } else {
+        for (int i = ctx->pending_nwin - 1; i >= 0; i--) {
+            for (int d = 0; d < ctx->pending_c; d++) acc = acc.dbl();
+            acc.add(w[i]);
+        }
     }
     point_to_bytes(acc, ctx->pending_fmt, out);
     return LURK_OK;
@@ -583,6 +663,7 @@ void lurk_msm_ctx_destroy(lurk_msm_ctx *ctx) {
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     if (ctx->done) cudaEventDestroy(ctx->done);
     if (ctx->owns_bases && ctx->d_bases) cudaFree(ctx->d_bases);
+    if (ctx->owns_table && ctx->d_table) cudaFree(ctx->d_table);
     delete ctx;
 }
 
@@ -606,6 +687,30 @@ int lurk_msm_ctx_finish(lurk_msm_ctx *ctx, uint8_t out_xyz[96]) {
     std::lock_guard<std::mutex> g(ctx->mu);
     return dispatch_curve(ctx->curve_id, [&](auto c) { return msm_finish<decltype(c)>(ctx, out_xyz); });
 }
+int lurk_msm_ctx_precompute(lurk_msm_ctx *ctx) {
+    if (!ctx) { set_error("null context"); return LURK_ERR_ARG; }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (ctx->d_table || ctx->n == 0) return LURK_OK;
+    if (ctx->pending) { set_error("a launch is pending on this context"); return LURK_ERR_ARG; }
+    return dispatch_curve(ctx->curve_id, [&](auto cv) {
+        using Cv = decltype(cv);
+        using Fb = typename Cv::Base;
+        const int c = fixed_base_window(ctx->n);
+        const int nwin = Cv::Scalar::Params::NBITS / c + 1;
+        if (nwin > MSM_MAX_TABLE_WINDOWS || (uint64_t)nwin * ctx->n >= (1ull << 31)) { set_error("commitment key too large for a fixed-base table"); return LURK_ERR_ARG; }
+        void *t = nullptr;
+        LURK_CUDA_TRY(cudaMalloc(&t, (size_t)nwin * ctx->n * sizeof(Affine<Fb>)));
+        msm_precompute_kernel<Fb><<<(unsigned)((ctx->n + 127) / 128), 128>>>((const Affine<Fb> *)ctx->d_bases, ctx->n, c, nwin, (Affine<Fb> *)t);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { cudaFree(t); set_error("fixed-base precomputation failed: %s", cudaGetErrorString(e)); return LURK_ERR_CUDA; }
+        ctx->d_table = t;
+        ctx->owns_table = true;
+        ctx->fixed_c = c;
+        return LURK_OK;
+    });
+}
+
 int lurk_msm_ctx_clone(lurk_msm_ctx *ctx, lurk_msm_ctx **out) {
     if (!ctx || !out) { set_error("null argument"); return LURK_ERR_ARG; }
     lurk_msm_ctx *c = new lurk_msm_ctx();
@@ -614,6 +719,9 @@ int lurk_msm_ctx_clone(lurk_msm_ctx *ctx, lurk_msm_ctx **out) {
     c->n = ctx->n;
     c->d_bases = ctx->d_bases;     // shared, not owned: the parent must outlive its clones
     c->owns_bases = false;
+    c->d_table = ctx->d_table;
+    c->owns_table = false;
+    c->fixed_c = ctx->fixed_c;
     *out = c;
     return LURK_OK;
 }

@@ -7,7 +7,7 @@ namespace lurk {
 
 struct PoseidonLayout {
     int rf, rp;
-    int off_mds, off_pre, off_sw, off_sv, off_cross, flat_len;   // in elements
+    int off_mds, off_pre, off_sw, off_sv, flat_len;   // in elements
     int block_elems;                                   // witness block size (arity + aux + 1)
 };
 

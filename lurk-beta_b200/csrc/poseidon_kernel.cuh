@@ -172,51 +172,29 @@ poseidon_kernel(const F *__restrict__ g_consts, PoseidonLayout L, F tag, const F
             // first-half rounds end with the pre-sparse matrix; the last round only needs the digest lane
             matvec<F, T>(S, C + (r == half - 1 ? L.off_pre : L.off_mds), last ? 1 : 0, last ? 2 : T);
             if (r != half - 1) continue;
-            // Partial rounds: S-box on lane 0, one sparse matrix each:  s0' = <w, s>,  s_j' = s_j + x * v_(j-1).
-            // Evaluated in groups of G rounds against the lanes sigma_j as they were at the start of the group:
-            //   s0'(q) = w0 x_q + <w^(q), sigma> + sum_(i<q) x_i * cross[q][i]      (one lazy reduction)
-            //   sigma_j += sum_(i<G) x_i * v^(i)_(j-1)                              (one lazy reduction per lane per GROUP)
-            // which replaces G (t-1) full Montgomery products by (t-1) G-term lazy dot products (-15% IMAD per round).
-            constexpr int G = PoseidonParams<F>::PARTIAL_GROUP;
+            // partial rounds: S-box on lane 0, one sparse matrix each
             F s0 = S.ld(0);
             const F *w = C + L.off_sw;
             const F *v = C + L.off_sv;
-            const F *cx = C + L.off_cross;
 #pragma unroll 1
-            for (int q0 = 0; q0 < L.rp; q0 += G) {
-                const int gl = min(G, L.rp - q0);
-                F x[G];
-#pragma unroll
-                for (int qq = 0; qq < G; qq++) {
-                    if (qq < gl) {
-                        F x2 = s0.sqr();
-                        F x4 = x2.sqr();
-                        x[qq] = x4 * s0 + lds_fe(key);
-                        key++;
-                        aux.put(x2); aux.put(x4); aux.put(x[qq]);
-                        WideAcc<typename F::Params> acc;
-                        acc.clear();
-                        acc.mul_acc(x[qq], lds_fe(w));
-#pragma unroll 1
-                        for (int j = 1; j < T; j++) acc.mul_acc(S.ld(j), lds_fe(w + j));
-#pragma unroll
-                        for (int i = 0; i < G - 1; i++)
-                            if (i < qq) acc.mul_acc(x[i], lds_fe(cx + i));
-                        s0 = acc.template reduce<(T + G - 1 > 11) ? 4 : 3>();   // up to T + G - 1 products
-                        w += T;
-                        cx += G - 1;
-                    }
-                }
+            for (int q = 0; q < L.rp; q++) {
+                F x2 = s0.sqr();
+                F x4 = x2.sqr();
+                s0 = x4 * s0 + lds_fe(key);
+                key++;
+                aux.put(x2); aux.put(x4); aux.put(s0);
+                WideAcc<typename F::Params> acc;
+                acc.clear();
+                acc.mul_acc(s0, lds_fe(w));
 #pragma unroll 1
                 for (int j = 1; j < T; j++) {
-                    WideAcc<typename F::Params> acc;
-                    acc.clear();
-#pragma unroll
-                    for (int i = 0; i < G; i++)
-                        if (i < gl) acc.mul_acc(x[i], lds_fe(v + i * (T - 1) + (j - 1)));
-                    S.st(j, S.ld(j) + acc.reduce());
+                    F x = S.ld(j);
+                    acc.mul_acc(x, lds_fe(w + j));
+                    S.st(j, x + s0 * lds_fe(v + (j - 1)));
                 }
-                v += gl * (T - 1);
+                s0 = acc.reduce();
+                w += T;
+                v += T - 1;
             }
             S.st(0, s0);
         }
@@ -301,7 +279,6 @@ static PoseidonInstance<F> &instance(int arity) {
         PoseidonLayout &L = inst->layout;
         L.rf = p.rf; L.rp = p.rp;
         L.off_mds = (int)p.off_mds(); L.off_pre = (int)p.off_pre(); L.off_sw = (int)p.off_sw(); L.off_sv = (int)p.off_sv();
-        L.off_cross = (int)p.off_cross();
         L.flat_len = (int)p.flat_len();
         L.block_elems = arity + p.num_aux() + 1;
         it = cache.emplace(arity, std::move(inst)).first;

@@ -76,19 +76,13 @@ struct PoseidonParams {
     std::vector<F> pre_sparse;        // t * t
     std::vector<F> sparse_w;          // rp * t       first column of each sparse factor
     std::vector<F> sparse_v;          // rp * (t - 1) rest of the first row of each sparse factor
-    // Partial rounds are evaluated in groups of PARTIAL_GROUP rounds against a stale copy of lanes 1..t-1 (see
-    // poseidon_kernel.cuh): cross[q * (G-1) + i] = sum_j w^(q)_j * v^(q0+i)_(j-1), q0 = first round of q's group,
-    // is the coefficient of the i-th S-box output of the group in the lane-0 dot product of round q.
-    static constexpr int PARTIAL_GROUP = 4;
-    std::vector<F> cross;             // rp * (PARTIAL_GROUP - 1), zero padded
 
-    // flat device image: [compressed | mds | pre_sparse | sparse_w | sparse_v | cross], Montgomery limbs
+    // flat device image: [compressed | mds | pre_sparse | sparse_w | sparse_v], Montgomery limbs
     size_t off_mds() const { return compressed.size(); }
     size_t off_pre() const { return off_mds() + (size_t)t * t; }
     size_t off_sw() const { return off_pre() + (size_t)t * t; }
     size_t off_sv() const { return off_sw() + (size_t)rp * t; }
-    size_t off_cross() const { return off_sv() + (size_t)rp * (t - 1); }
-    size_t flat_len() const { return off_cross() + (size_t)rp * (PARTIAL_GROUP - 1); }
+    size_t flat_len() const { return off_sv() + (size_t)rp * (t - 1); }
     std::vector<F> flat() const {
         std::vector<F> o;
         o.reserve(flat_len());
@@ -97,7 +91,6 @@ struct PoseidonParams {
         o.insert(o.end(), pre_sparse.begin(), pre_sparse.end());
         o.insert(o.end(), sparse_w.begin(), sparse_w.end());
         o.insert(o.end(), sparse_v.begin(), sparse_v.end());
-        o.insert(o.end(), cross.begin(), cross.end());
         return o;
     }
     int num_aux() const { return 3 * (t * rf + rp); }
@@ -234,19 +227,6 @@ PoseidonParams<F> make_poseidon_params(int arity) {
     for (int r = rp - 1; r >= 0; r--) {
         pp.sparse_w.insert(pp.sparse_w.end(), ws[r].begin(), ws[r].end());
         pp.sparse_v.insert(pp.sparse_v.end(), vs[r].begin(), vs[r].end());
-    }
-    // cross coefficients of the grouped evaluation (rounds indexed in application order)
-    constexpr int G = PoseidonParams<F>::PARTIAL_GROUP;
-    pp.cross.assign((size_t)rp * (G - 1), F::zero());
-    for (int q = 0; q < rp; q++) {
-        const int q0 = (q / G) * G;
-        const F *w = &pp.sparse_w[(size_t)q * t];
-        for (int i = 0; q0 + i < q; i++) {
-            const F *v = &pp.sparse_v[(size_t)(q0 + i) * (t - 1)];
-            F c = F::zero();
-            for (int j = 1; j < t; j++) c = c + w[j] * v[j - 1];
-            pp.cross[(size_t)q * (G - 1) + i] = c;
-        }
     }
     return pp;
 }

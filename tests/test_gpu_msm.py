@@ -122,3 +122,22 @@ def test_msm_async_launch_finish_and_clone(L, oracle, spec):
         ck.finish()                                                                         # nothing pending
     ms, launches = ck.last_profile()
     assert launches >= 10
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_msm_fixed_base_table_same_results(L, oracle, spec, curve):
+    """fixed-base mode (window multiples precomputed, shared bucket set) must not change any result"""
+    n = 40_000
+    bases = oracle.gen_bases(curve, n)
+    bases[64 * 3:64 * 4] = 0                                   # identity base survives the table build
+    q = spec.FIELD_MODULUS[spec.CURVES[curve]["scalar"]]
+    ck = L.CommitmentKey(curve, bases).precompute()
+    for seed, shape in ((1, "uniform"), (2, "witness")):
+        sc = scalars_for(spec, curve, n, seed=seed, shape=shape)
+        assert np.array_equal(ck.commit(sc), oracle.msm(curve, bases, sc, nthreads=8))
+    for vals in ([q - 1] * 257, [1] * 100, [0] * 10, [(1 << 253) + 12345] * 33):
+        sc = pack(vals)
+        assert np.array_equal(ck.commit(sc), oracle.msm(curve, bases[:64 * len(vals)], sc))
+    clone = ck.clone()
+    sc = scalars_for(spec, curve, 1000, seed=9, shape="uniform")
+    assert np.array_equal(clone.commit(sc), oracle.msm(curve, bases[:64000], sc))

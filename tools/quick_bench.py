@@ -40,13 +40,15 @@ def poseidon(field, arity, logn):
           f"{n * (arity + 1) * 32 / best / 1e6:.1f} GB/s algorithmic", flush=True)
 
 
-def msm(curve, logn, shape):
+def msm(curve, logn, shape, fixed=False):
     n = 1 << logn
     from oracle import spec
     t0 = time.time()
     bases = oracle.gen_bases(curve, n)
     sc = random_elements(spec.CURVES[curve]["scalar"], n, seed=2, shape=shape)
     ck = L.CommitmentKey(curve, bases)
+    if fixed:
+        ck.precompute()
     d_sc = torch.from_numpy(sc).cuda()
     out = None
 
@@ -54,7 +56,7 @@ def msm(curve, logn, shape):
         nonlocal out
         out = ck.commit_device(d_sc.data_ptr(), n, fmt=0)
     best, med = timeit(fn, reps=5, warm=2)
-    print(f"msm curve={curve} n=2^{logn} {shape}: best {best:.2f} ms med {med:.2f} ms -> {n / best / 1e3:.2f} Mterm/s, "
+    print(f"msm curve={curve} n=2^{logn} {shape}{' fixed-base' if fixed else ''}: best {best:.2f} ms med {med:.2f} ms -> {n / best / 1e3:.2f} Mterm/s, "
           f"{n * 96 / best / 1e6:.1f} GB/s algorithmic (setup {time.time() - t0:.1f}s)", flush=True)
 
 
@@ -72,3 +74,5 @@ if __name__ == "__main__":
     if which in ("all", "msm"):
         for c, ln, sh in [(0, 16, "uniform"), (0, 20, "uniform"), (0, 20, "witness"), (2, 20, "uniform"), (0, 21, "witness")]:
             msm(c, ln, sh)
+        for c, ln, sh in [(0, 20, "uniform"), (0, 21, "witness")]:
+            msm(c, ln, sh, fixed=True)
