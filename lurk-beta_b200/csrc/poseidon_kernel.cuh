@@ -206,6 +206,134 @@ poseidon_kernel(const F *__restrict__ g_consts, PoseidonLayout L, F tag, const F
     }
 }
 
+// ----------------------------------------------------------------------------- warp-per-sponge (latency shape)
+// Small batches (the few thousand slots of one fold, one level of the store DAG) are latency bound with one thread per
+// sponge: ~1e5..2e5 dependent multiplier instructions.  Here T = arity + 1 adjacent lanes own one sponge, one state
+// element per lane, floor(32 / T) sponges per warp:
+//   full round    every lane does its own S-box; lane j gathers the T post-S-box elements with warp shuffles and
+//                 computes column j of state * M as one lazy dot product (T word products deep instead of T^2 + 3T);
+//   partial round lane 0's S-box, its result broadcast; every lane forms its term of <w, s> and its own update
+//                 s_j + x v_(j-1) concurrently; the T terms are summed by a shuffle tree.
+// ~4x lower latency than the thread-per-sponge kernel at ~1/3 of its throughput, so it is used only for small n.
+template <class F>
+__device__ __forceinline__ F shfl_fe(const F &x, int src_lane) {
+    F r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, x.v[i], src_lane);
+    return r;
+}
+template <class F>
+__device__ __forceinline__ F shfl_down_fe(const F &x, int d) {
+    F r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, x.v[i], d);
+    return r;
+}
+
+template <class F, int ARITY, bool WITNESS>
+__global__ void __launch_bounds__(128)
+poseidon_warp_kernel(const F *__restrict__ g_consts, PoseidonLayout L, F tag, const F *__restrict__ pre, size_t n,
+                     F *__restrict__ out, int in_fmt, int out_fmt) {
+    constexpr int T = ARITY + 1;
+    constexpr int GPW = 32 / T;   // sponges per warp
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    F *C = reinterpret_cast<F *>(smem_raw);
+    const int tid = threadIdx.x;
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)L.flat_len * (uint32_t)sizeof(F);
+        mbar_expect_tx(&mbar, bytes);
+        bulk_g2s(C, g_consts, bytes, &mbar);
+    }
+    mbar_wait(&mbar, 0);
+
+    const int lane = tid & 31;
+    const int g = lane / T, i = lane - g * T;         // sponge within the warp, state element
+    const int base_lane = g * T;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + tid) >> 5;
+    const size_t h = warp * GPW + g;
+    const bool live = g < GPW && h < n;                // idle lanes run the same code on zeros and never store
+    const int half = L.rf / 2;
+
+    F *wout = (WITNESS && live) ? out + h * (size_t)L.block_elems : nullptr;
+    const bool mont_out = out_fmt == LURK_FMT_MONTGOMERY;
+    // absorb
+    F s = tag;
+    if (i > 0) {
+        F raw = live ? load_fe<F>(pre + h * ARITY + (i - 1)) : F::zero();
+        s = in_fmt == LURK_FMT_MONTGOMERY ? raw : F::from_canonical(raw);
+        if (WITNESS && live) store_fe(wout + (i - 1), mont_out ? s : (in_fmt == LURK_FMT_MONTGOMERY ? s.to_canonical() : raw));
+    }
+    s = s + lds_fe(C + i);
+    const F *key = C + T;
+    int aux = ARITY;                                   // next free element of the witness block
+
+#pragma unroll 1
+    for (int r = 0; r < L.rf; r++) {
+        const bool last = r == L.rf - 1;
+        {   // S-box on every lane
+            F x2 = s.sqr();
+            F x4 = x2.sqr();
+            s = x4 * s;
+            if (!last) s = s + lds_fe(key + i);
+            if (WITNESS && live) {
+                F *o = wout + aux + 3 * i;
+                store_fe(o, mont_out ? x2 : x2.to_canonical());
+                store_fe(o + 1, mont_out ? x4 : x4.to_canonical());
+                store_fe(o + 2, mont_out ? s : s.to_canonical());
+            }
+            aux += 3 * T;
+            if (!last) key += T;
+        }
+        {   // column i of state * M
+            const F *M = C + (r == half - 1 ? L.off_pre : L.off_mds);
+            WideAcc<typename F::Params> acc;
+            acc.clear();
+#pragma unroll 1
+            for (int m = 0; m < T; m++) acc.mul_acc(shfl_fe(s, base_lane + m), lds_fe(M + m * T + i));
+            s = acc.reduce();
+        }
+        if (r != half - 1) continue;
+        // partial rounds
+        const F *w = C + L.off_sw;
+        const F *v = C + L.off_sv;
+#pragma unroll 1
+        for (int q = 0; q < L.rp; q++) {
+            F x2 = s.sqr();                            // only lane 0's S-box is used; the others keep lock step
+            F x4 = x2.sqr();
+            F x = x4 * s + lds_fe(key);
+            key++;
+            if (WITNESS && live && i == 0) {
+                F *o = wout + aux;
+                store_fe(o, mont_out ? x2 : x2.to_canonical());
+                store_fe(o + 1, mont_out ? x4 : x4.to_canonical());
+                store_fe(o + 2, mont_out ? x : x.to_canonical());
+            }
+            aux += 3;
+            x = shfl_fe(x, base_lane);                 // lane 0's S-box output
+            F term = (i == 0 ? x : s) * lds_fe(w + i); // term i of <w, s'>
+            F upd = s;
+            if (i > 0) upd = s + x * lds_fe(v + (i - 1));
+            // sum the T terms into lane 0 of the group
+#pragma unroll
+            for (int d = 1; d < T; d <<= 1) {
+                F t2 = shfl_down_fe(term, d);
+                if (i + d < T) term = term + t2;
+            }
+            s = i == 0 ? term : upd;
+            w += T;
+            v += T - 1;
+        }
+    }
+    if (live && i == 1) {
+        F d = mont_out ? s : s.to_canonical();
+        if (WITNESS) store_fe(wout + aux, d);
+        else store_fe(out + h, d);
+    }
+}
+
 // ----------------------------------------------------------------------------- bit decomposition slots
 // aux order of bellpepper-core AllocatedNum::to_bits_le_strict (call site src/lem/circuit.rs:241-243) preceded by
 // the slot's preimage element: walking the bits of p-1 from the top, a bit under a 1 of p-1 is allocated and
@@ -337,7 +465,24 @@ static int launch_arity(const void *d_pre, size_t n, void *d_out, int in_fmt, in
         // throughput shape: one persistent CTA per SM
         return launch_one<F, ARITY, WITNESS>(d_consts, inst, d_pre, n, d_out, in_fmt, out_fmt, sms, BIG, s);
     }
-    // latency shape (slot batches of a few thousand sponges): spread single warps over the SMs
+    if (n <= 8192) {
+        // latency shape (the slot batches of one fold, one level of the store DAG): warp-per-sponge kernel
+        constexpr int GPW = 32 / (ARITY + 1);
+        const size_t warps = (n + GPW - 1) / GPW;
+        const unsigned grid = (unsigned)((warps + 3) / 4);
+        auto kern = poseidon_warp_kernel<F, ARITY, WITNESS>;
+        const size_t smem = (size_t)inst.layout.flat_len * sizeof(F);
+        static std::once_flag once[16];
+        int dev = 0;
+        LURK_CUDA_TRY(cudaGetDevice(&dev));
+        cudaError_t attr_err = cudaSuccess;
+        std::call_once(once[dev & 15], [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+        LURK_CUDA_TRY(attr_err);
+        kern<<<grid, 128, smem, s>>>(d_consts, inst.layout, inst.params.domain_tag, (const F *)d_pre, n, (F *)d_out, in_fmt, out_fmt);
+        LURK_CUDA_TRY(cudaGetLastError());
+        return LURK_OK;
+    }
+    // medium batches: thread-per-sponge, single warps spread over the SMs
     int grid = (int)((n + 31) / 32);
     return launch_one<F, ARITY, WITNESS>(d_consts, inst, d_pre, n, d_out, in_fmt, out_fmt, grid, 32, s);
 }
