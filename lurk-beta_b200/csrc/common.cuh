@@ -86,5 +86,6 @@ inline int sm_count() {
 template <class F> int convert_dev(const void *d_in, size_t n, int to_fmt, void *d_out, cudaStream_t s);
 // returns number of elements >= p in a raw host/device buffer check (device side), used by host entry points
 template <class F> int check_reduced_dev(const void *d_in, size_t n, cudaStream_t s, int *bad_host);
+template <class F> int check_reduced_accumulate_dev(const void *d_in, size_t n, cudaStream_t s, int *d_bad);
 
 }  // namespace lurk

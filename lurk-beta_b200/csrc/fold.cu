@@ -55,6 +55,15 @@ int check_reduced_dev(const void *d_in, size_t n, cudaStream_t s, int *bad_host)
     return LURK_OK;
 }
 
+// asynchronous variant: adds the number of unreduced elements to *d_bad (device counter) on stream s
+template <class F>
+int check_reduced_accumulate_dev(const void *d_in, size_t n, cudaStream_t s, int *d_bad) {
+    if (n == 0) return LURK_OK;
+    check_reduced_kernel<F><<<stream_grid(n, 256, 8), 256, 0, s>>>((const F *)d_in, n, d_bad);
+    LURK_CUDA_TRY(cudaGetLastError());
+    return LURK_OK;
+}
+
 // out[i] = a[i] + r * b[i]
 template <class F>
 __global__ void __launch_bounds__(256) axpy_kernel(const F *__restrict__ a, const F *__restrict__ b, F r, size_t n, F *__restrict__ out) {
@@ -99,7 +108,8 @@ template <class F> static F fe_from_bytes(const uint8_t b[32]) { F x; memcpy(x.v
 
 #define LURK_FOLD_INSTANTIATE(F)                                                         \
     template int convert_dev<F>(const void *, size_t, int, void *, cudaStream_t);        \
-    template int check_reduced_dev<F>(const void *, size_t, cudaStream_t, int *);
+    template int check_reduced_dev<F>(const void *, size_t, cudaStream_t, int *);         \
+    template int check_reduced_accumulate_dev<F>(const void *, size_t, cudaStream_t, int *);
 LURK_FOLD_INSTANTIATE(Fe<Bn254Fr>)
 LURK_FOLD_INSTANTIATE(Fe<Bn254Fq>)
 LURK_FOLD_INSTANTIATE(Fe<PallasFq>)

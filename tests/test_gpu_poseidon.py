@@ -124,3 +124,46 @@ def test_generate_slots_witnesses_frame_layout(L, oracle):
         else:
             want = oracle.poseidon_witness_batch(0, st.preimg_size(), pack(pre))
         assert np.array_equal(blk, want)
+
+
+def test_slot_witness_chunked_host_pipeline(L, oracle):
+    # > 48 MB of witness output: the host-buffer entry point streams chunks through its pinned staging slots
+    field, arity, n = 0, 8, 9000
+    pre = random_elements(field, n * arity, seed=123, shape="lem")
+    got = L.slot_witness_batch_bytes(field, L.SlotType.Hash8, pre)
+    assert got.size == n * 396 * 32
+    assert np.array_equal(got, oracle.poseidon_witness_batch(field, arity, pre, nthreads=8))
+    # a bad element in the last chunk is still reported
+    bad = pre.copy()
+    bad[-32:] = 0xff
+    with pytest.raises(L.LurkError) as e:
+        L.slot_witness_batch_bytes(field, L.SlotType.Hash8, bad)
+    assert e.value.code == L._capi.ERR_RANGE
+
+
+def test_concurrent_callers(L, oracle):
+    """the seams are called from rayon workers and the witness thread concurrently (src/proof/nova.rs:297-326):
+    every entry point must be re-entrant"""
+    import threading
+    jobs = [(0, 4, 3000, 1), (0, 8, 2000, 2), (2, 4, 2500, 3), (0, 3, 1000, 4), (0, 4, 200_000, 5), (2, 8, 1500, 6)]
+    results, errors = {}, []
+
+    def work(k, field, arity, n, seed):
+        try:
+            pre = random_elements(field, n * arity, seed=seed)
+            pc = L.PoseidonCache(field)
+            for _ in range(3):
+                results[k] = (pre, pc.hash_batch_bytes(arity, pre))
+        except Exception as ex:       # noqa: BLE001
+            errors.append(ex)
+
+    threads = [threading.Thread(target=work, args=(k, *j)) for k, j in enumerate(jobs)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k, (field, arity, n, _seed) in enumerate(jobs):
+        pre, got = results[k]
+        m = min(n, 3000)
+        assert np.array_equal(got[:m * 32], oracle.poseidon_hash_batch(field, arity, pre[:m * arity * 32], nthreads=4))
