@@ -151,3 +151,25 @@ class NovaFoldPipeline:
     def drain(self, b):
         """collect a prefetched commit(W) that will not be folded"""
         return self.ckW[b].finish()
+
+
+class SuperNovaFoldPipeline:
+    """NIVC form (reference src/proof/supernova.rs:207-291): one running instance per circuit -- the Lurk step circuit
+    plus one per coprocessor -- and every step folds into the instance selected by `MultiFrame::circuit_index()`
+    (src/lem/multiframe.rs:941).  Each circuit has its own R1CS shape, witness length and buffers; they share the
+    device-resident commitment key (sized for the largest circuit).  Stage A of the next step may belong to a different
+    circuit than the step being folded; the two never touch the same buffers."""
+
+    def __init__(self, pipelines):
+        self.pipelines = list(pipelines)          # NovaFoldPipeline per circuit index, all built on clones of one key
+        self._buf = [0] * len(self.pipelines)     # next double-buffer slot per circuit
+
+    def stage_a(self, circuit_index, slot_batches, before=None):
+        p = self.pipelines[circuit_index]
+        b = self._buf[circuit_index]
+        p.stage_a(b, slot_batches, before)
+        self._buf[circuit_index] ^= 1
+        return b
+
+    def stage_b(self, circuit_index, b, challenge):
+        return self.pipelines[circuit_index].stage_b(b, challenge)

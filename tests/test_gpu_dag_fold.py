@@ -150,3 +150,25 @@ def test_ntt_rejects_unsupported_size(L):
     import torch
     d = torch.zeros(64, dtype=torch.uint8, device="cuda")
     assert L._capi.lib().lurk_ntt_dev(L.FIELD_BN254_FQ, d.data_ptr(), 2, 0, None) == L._capi.ERR_ARG   # 2-adicity 1
+
+
+def test_trie_coprocessor_mirror_goldens(L, oracle):
+    """trie coprocessor hashing through the CUDA path: empty roots (trie/mod.rs:925-1010), empty StandardTrie root,
+    insert golden (eval_tests.rs:3868,3904), lookup, and the 85 batched lookup-circuit witnesses (a12)."""
+    pc = L.PoseidonCache(L.FIELD_BN254_FR)
+    small = L.Trie(pc, 8, 3)
+    assert [small.empty_root_for_height(k) for k in (0, 1, 2, 3)] == [0, GOLDEN["G1"], GOLDEN["G2"], GOLDEN["G3"]]
+    assert small.path(500) == [7, 6, 4]                                   # test_path
+    assert L.Trie(pc, 8, 4).empty_root() == GOLDEN["G4"]
+    t = L.StandardTrie(pc)
+    assert t.root == t.empty_root() == GOLDEN["G5"]
+    assert t.lookup(123) is None
+    assert t.insert(123, 456) is True
+    from util import GOLDEN as G
+    assert t.root == G["G10"]
+    assert t.lookup(123) == 456 and t.lookup(124) is None
+    assert t.insert(123, 456) is False                                    # same value: root unchanged
+    w = t.lookup_circuit_witnesses(123)
+    assert w.size == 85 * 396 * 32                                        # 85 x hash8 slot blocks (a12: ~1.08 MB of aux)
+    pre = pack([x for p in t.prove_lookup_at_path(t.path(123)) for x in p])
+    assert np.array_equal(w, oracle.poseidon_witness_batch(0, 8, pre, nthreads=4))

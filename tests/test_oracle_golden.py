@@ -164,3 +164,23 @@ def test_dag_oracle_matches_flat_hashes(oracle, spec):
     d0 = spec.hash_correct(0, [5, 11, 6, 22])
     d1 = spec.hash_correct(0, [33, 7, d0, 11])
     assert out == [d0, d1, spec.hash_correct(0, [22, 4, d1])]
+
+
+def test_trie_insert_golden(oracle):
+    """G10: root of the StandardTrie (arity 8, height 85) after inserting 123 -> 456 (src/lem/tests/eval_tests.rs:3904,
+    src/proof/tests/nova_tests.rs:4351); path = 3-bit chunks of the key, most significant first (trie/mod.rs:589-609,
+    test_path: path(500) at height 3 = [7, 6, 4])."""
+    height, arity, key, value = 85, 8, 123, 456
+    path = lambda k, hgt: [(k >> (3 * (hgt - 1 - i))) & 7 for i in range(hgt)]
+    assert path(500, 3) == [7, 6, 4]
+    empty = [0]
+    for _ in range(height):
+        empty.append(h(oracle, BN, [empty[-1]] * arity))
+    assert empty[85] == GOLDEN["G5"]
+    # on the empty trie the node at depth d on any path has 8 children equal to empty[height - d - 1]
+    v = value
+    for depth in reversed(range(height)):
+        pre = [empty[height - depth - 1]] * arity
+        pre[path(key, height)[depth]] = v
+        v = h(oracle, BN, pre)
+    assert v == GOLDEN["G10"]

@@ -12,6 +12,7 @@ GOLDEN = {   # reference golden digests, BN256 Fr
     "G6": 0x1d501baeefe83acf0e7137180b091834f542a5059dbaf99ec82c5e19d3bb9201,   # src/lem/store.rs:1473
     "G7": 0x0df269cc1a453b80d4694fe3e54f0ff2d68bfa6a6dd6320446af03691112e89d,   # src/lem/tests/eval_tests.rs:1944
     "G8": 0x2e78db30531cf5ddd836d2b5594d2895a78c71de06abf212c4bcb0de268d4557,   # src/lem/tests/eval_tests.rs:1955
+    "G10": 0x21ad1dd339f26bb824ab861dbcf110c1bcb3b7658eea4b5e84780a3b4958bf95,  # StandardTrie root after insert 123 -> 456 (eval_tests.rs:3904)
 }
 # ExprTag values used by the goldens (src/tag.rs): Nil=0, Cons=1, Sym=2, Fun=3, Num=4, Str=6, Char=7
 TAG_SYM, TAG_NUM, TAG_STR, TAG_CHAR, TAG_NIL = 2, 4, 6, 7, 0
