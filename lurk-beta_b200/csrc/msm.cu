@@ -574,11 +574,13 @@ static int msm_finish(lurk_msm_ctx *ctx, uint8_t out[96]) {
     const Pt *w = reinterpret_cast<const Pt *>(ctx->scratch.h_wins);
     Pt acc = Pt::identity();
     if (ctx->pending_fixed) {
-        // shared bucket set cut into virtual windows: sum_v (R_v + (v * nb) * S_v)
-        for (uint32_t v = 0; v < ctx->pending_vwin; v++) {
-            acc.add(w[v]);
-            if (v) acc.add(w[64 + v].mul_u32(v * ctx->pending_nb));
-        }
+        // shared bucket set cut into virtual windows: sum_v R_v + nb * sum_v v S_v; the weighted sum is a running sum
+        // over the (<= 16) virtual windows, nb is a power of two
+        Pt run = Pt::identity(), wsum = Pt::identity();
+        for (uint32_t v = ctx->pending_vwin; v-- > 1;) { run.add(w[64 + v]); wsum.add(run); }
+        for (uint32_t b = ctx->pending_nb; b > 1; b >>= 1) wsum = wsum.dbl();
+        for (uint32_t v = 0; v < ctx->pending_vwin; v++) acc.add(w[v]);
+        acc.add(wsum);
     } else {
         for (int i = ctx->pending_nwin - 1; i >= 0; i--) {
             for (int d = 0; d < ctx->pending_c; d++) acc = acc.dbl();
