@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- Lurk reduction iterations proved per second on the GPU hot path (BASELINE.json metric).
 
-Workload (default, `--workload fold`): the per-fold GPU work of `benches/fibonacci.rs` at rc = 100 (Nova IVC, BN254 /
+Workload: the per-fold GPU work of `benches/fibonacci.rs` at rc = 100 (Nova IVC, BN254 /
 Grumpkin cycle as the reference bench really runs -- SURVEY.md D1), composed from the kernels of SURVEY.md 8(a) exactly
 as RecursiveSNARK::prove_step uses them, on synthetic inputs of the real shapes:
     K3  slot witnesses: 1400 Hash4 + 600 Hash8 + 100 Commitment Poseidon witnesses + 300 bit decompositions per step
@@ -143,7 +143,7 @@ class FoldStepGPU:
         del bases
         self.ck2 = L.CommitmentKey(CURVE2, L.synthetic_bases(CURVE2, 1 << 14, fmt=L.FMT_MONTGOMERY), fmt=L.FMT_MONTGOMERY)
         # ---- slot preimages (host, pinned: what the CPU gather hands over every step)
-        self.slot_pre_host, self.slot_pre_dev, self.slot_out = {}, {}, {}
+        self.slot_pre_host, self.slot_pre_dev = {}, {}
         self.slot_region = 0
         offs = 0
         self.slot_layout = []

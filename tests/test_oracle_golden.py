@@ -56,6 +56,10 @@ def test_structural_zero_tuples(oracle, spec):
 
 
 def test_witness_sizes_pinned_by_reference(oracle, spec):
+    from util import REFERENCE
+    sz = REFERENCE["sizes"]
+    assert [oracle.witness_block(BN, a) for a in (4, 6, 8, 3)] == [sz["slot_witness_elements_bn256"][k] for k in ("Hash4", "Hash6", "Hash8", "Commitment")]
+    assert [oracle.bitdecomp_size(f) for f in (2, 3, 0, 1)] == [sz["bit_decomp_witness_elements"][k] for k in ("pallas", "vesta", "bn256", "grumpkin")]
     # src/lem/multiframe.rs:991-1016 / src/lem/eval.rs:1960-1967: 14*293 + 6*396 + 268 + 3*354 = 7808 (BN256)
     assert [oracle.witness_block(BN, a) for a in (4, 6, 8, 3)] == [293, 343, 396, 268]
     assert 14 * 293 + 6 * 396 + 268 + 3 * oracle.bitdecomp_size(BN) == 7808

@@ -3,17 +3,13 @@ import numpy as np
 
 from oracle import spec
 
-GOLDEN = {   # reference golden digests, BN256 Fr
-    "G1": 0x1ca5b207085f3f0f324a2e0704b18fff1cda2e2d686aa85343fea91df77bf35b,   # src/coprocessor/trie/mod.rs:932,983
-    "G2": 0x0637ddaef5cd53ba6711c328952208d846222066701e10c34d3a6df7350de8aa,   # :936,992
-    "G3": 0x08127a45502f5939273edd1957c8748ae39992e2a459d99f999992a842df99a5,   # :940,1001
-    "G4": 0x12c2ef2ab5df25442fe23d8711bf985f02c39e83930517f7103d4bd4228c6cfb,   # :1010
-    "G5": 0x2bfc4f437d5ca652511d67e06201b4fdf95c314c85ea987988746a253071bed6,   # src/lem/tests/eval_tests.rs:3868
-    "G6": 0x1d501baeefe83acf0e7137180b091834f542a5059dbaf99ec82c5e19d3bb9201,   # src/lem/store.rs:1473
-    "G7": 0x0df269cc1a453b80d4694fe3e54f0ff2d68bfa6a6dd6320446af03691112e89d,   # src/lem/tests/eval_tests.rs:1944
-    "G8": 0x2e78db30531cf5ddd836d2b5594d2895a78c71de06abf212c4bcb0de268d4557,   # src/lem/tests/eval_tests.rs:1955
-    "G10": 0x21ad1dd339f26bb824ab861dbcf110c1bcb3b7658eea4b5e84780a3b4958bf95,  # StandardTrie root after insert 123 -> 456 (eval_tests.rs:3904)
-}
+import json
+import os
+
+# reference golden digests, BN256 Fr; the fixture cites the reference test each one comes from
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_goldens.json")) as _f:
+    REFERENCE = json.load(_f)
+GOLDEN = {k: int(v["hex"], 16) for k, v in REFERENCE["poseidon_digests"].items()}
 # ExprTag values used by the goldens (src/tag.rs): Nil=0, Cons=1, Sym=2, Fun=3, Num=4, Str=6, Char=7
 TAG_SYM, TAG_NUM, TAG_STR, TAG_CHAR, TAG_NIL = 2, 4, 6, 7, 0
 
