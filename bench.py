@@ -359,7 +359,11 @@ def run_gpu(args):
             "gpu_launches": int(wl.launches * args.steps),
             "roofline": {"kernel": "msm_accumulate_kernel (bucket accumulation of commit(W) / commit(T))", "bound": "hbm",
                          "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
-                         "traffic": None, "avg_launch_ms": round(iso_ms, 4), "avg_launch_ms_overlapped_in_step": round(avg_ms, 4), "algorithmic_bytes_per_launch": int(terms * 96),
+                         "traffic": (1.92e9 if not args.no_fixed_base else 1.16e9),
+                         "traffic_note": "dram__bytes_read+write per launch from profiles/r1_ncu_full_msm_fixed_raw.csv (fixed-base) / "
+                                         "r1_ncu_full_msm_raw_final.csv; Pippenger gathers each 64-byte base once per window (13 x 64 B + index per term), "
+                                         "so traffic is ~19x the 96 B/term algorithmic figure by construction, still 10 % of DRAM bandwidth",
+                         "avg_launch_ms": round(iso_ms, 4), "avg_launch_ms_overlapped_in_step": round(avg_ms, 4), "algorithmic_bytes_per_launch": int(terms * 96),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "note": "bound by the FMA-heavy (IMAD.WIDE) pipe, 85-89 % busy in the ncu captures (profiles/): ~13 bucket "
                                  "additions x ~1.4e3 IMAD.WIDE per 96 algorithmic bytes; launch time = CUDA events inside the library on "
