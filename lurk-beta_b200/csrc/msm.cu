@@ -418,7 +418,12 @@ __global__ void __launch_bounds__(256) msm_bases_to_mont_kernel(Fb *coords, size
 struct MsmScratch {
     DevBuf counts, offsets, tiles, sorted, buckets, pkey[2], ppt[2], chunks, chunk_sums, wins, scalars;
     void *h_wins = nullptr;   // pinned
-    ~MsmScratch() { if (h_wins) cudaFreeHost(h_wins); }
+    void *h_stage[2] = {nullptr, nullptr};          // pinned staging for host-buffer scalars
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    ~MsmScratch() {
+        if (h_wins) cudaFreeHost(h_wins);
+        for (int k = 0; k < 2; k++) { if (h_stage[k]) cudaFreeHost(h_stage[k]); if (stage_done[k]) cudaEventDestroy(stage_done[k]); }
+    }
 };
 
 }  // namespace lurk
@@ -735,7 +740,24 @@ int lurk_msm_ctx_run(lurk_msm_ctx *ctx, const uint8_t *scalars, size_t n, int fm
     if (fmt != LURK_FMT_CANONICAL && fmt != LURK_FMT_MONTGOMERY) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
     std::lock_guard<std::mutex> g(ctx->mu);
     if (ctx->scratch.scalars.bytes < n * 32) LURK_TRY(ctx->scratch.scalars.alloc(n * 32));
-    LURK_CUDA_TRY(cudaMemcpy(ctx->scratch.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice));
+    // upload through two pinned staging buffers: the memcpy out of the caller's pageable memory overlaps the DMA
+    MsmScratch &S = ctx->scratch;
+    const size_t STAGE = (size_t)8 << 20;
+    if (!S.h_stage[0]) {
+        for (int k = 0; k < 2; k++) {
+            LURK_CUDA_TRY(cudaMallocHost(&S.h_stage[k], STAGE));
+            LURK_CUDA_TRY(cudaEventCreateWithFlags(&S.stage_done[k], cudaEventDisableTiming));
+        }
+    }
+    const size_t total = n * 32;
+    int k = 0;
+    for (size_t off = 0; off < total; off += STAGE, k ^= 1) {
+        const size_t len = std::min(STAGE, total - off);
+        LURK_CUDA_TRY(cudaEventSynchronize(S.stage_done[k]));      // the previous DMA out of this buffer is complete
+        memcpy(S.h_stage[k], scalars + off, len);
+        LURK_CUDA_TRY(cudaMemcpyAsync((uint8_t *)S.scalars.p + off, S.h_stage[k], len, cudaMemcpyHostToDevice, nullptr));
+        LURK_CUDA_TRY(cudaEventRecord(S.stage_done[k], nullptr));
+    }
     int bad = 0;
     LURK_TRY(dispatch_curve(ctx->curve_id, [&](auto c) {
         using Fs = typename decltype(c)::Scalar;
