@@ -142,11 +142,13 @@ class FoldStepGPU:
         self.ck.set_profiling(True)
         del bases
         self.ck2 = L.CommitmentKey(CURVE2, L.synthetic_bases(CURVE2, 1 << 14, fmt=L.FMT_MONTGOMERY), fmt=L.FMT_MONTGOMERY)
-        # ---- slot preimages (host, pinned: what the CPU gather hands over every step)
+        # ---- slot preimages (host, pinned: what the CPU gather hands over every step).  W is laid out as the reference
+        # lays it out (synthesize_frames_parallel, src/lem/multiframe.rs:635-712): per frame [14 Hash4 blocks | 6 Hash8 |
+        # 1 Commitment | 3 BitDecomp | 1311 LEM-body aux] = 9119 elements; the kernels scatter each block to its place.
         self.slot_pre_host, self.slot_pre_dev = {}, {}
-        self.slot_region = 0
-        offs = 0
         self.slot_layout = []
+        self.bd_block = self.lib.lurk_bitdecomp_witness_block(FIELD)
+        frame_off = 0
         for arity, per_frame in SLOTS:
             n = RC * per_frame
             pre = rand_elements(rng, n * arity).reshape(n, arity * 32)
@@ -155,21 +157,24 @@ class FoldStepGPU:
             blk = self.lib.lurk_poseidon_witness_block(FIELD, arity)
             self.slot_pre_host[arity] = torch.from_numpy(pre.reshape(-1)).pin_memory()
             self.slot_pre_dev[arity] = self.slot_pre_host[arity].cuda()
-            self.slot_layout.append((arity, n, offs, blk))
-            offs += n * blk
+            offs = (np.arange(RC, dtype=np.uint64)[:, None] * AUX_PER_FRAME + frame_off + np.arange(per_frame, dtype=np.uint64)[None, :] * blk).reshape(-1)
+            self.slot_layout.append((arity, n, torch.from_numpy(offs).cuda(), blk))
+            frame_off += per_frame * blk
         nbd = RC * BITDECOMP_PER_FRAME
-        self.bd_block = self.lib.lurk_bitdecomp_witness_block(FIELD)
         self.bd_host = torch.from_numpy(rand_elements(rng, nbd, "witness")).pin_memory()
         self.bd_dev = self.bd_host.cuda()
-        self.bd_n, self.bd_off = nbd, offs
-        offs += nbd * self.bd_block
-        self.slot_region = offs                       # 7808 * rc elements
-        assert self.slot_region == RC * 7808
+        self.bd_n = nbd
+        offs = (np.arange(RC, dtype=np.uint64)[:, None] * AUX_PER_FRAME + frame_off + np.arange(BITDECOMP_PER_FRAME, dtype=np.uint64)[None, :] * self.bd_block).reshape(-1)
+        self.bd_offs = torch.from_numpy(offs).cuda()
+        frame_off += BITDECOMP_PER_FRAME * self.bd_block
+        self.slot_per_frame = frame_off                # 7808 slot-witness elements per frame
+        assert self.slot_per_frame == 7808
+        self.glue_per_frame = AUX_PER_FRAME - self.slot_per_frame
         # ---- witness vectors (Montgomery, device resident).  z = (W, u, X0, X1); W1 / W2 are views into z1 / z2 so the
         # SpMVs read them in place.  The fresh-instance side (W2, Az2..Cz2) is double buffered: slot witnesses and
         # commit(W) of step i+1 are chain independent and run ahead of the fold of step i, as the
         # reference's witness thread does (src/proof/nova.rs:297-326).
-        glue = self.nW - self.slot_region
+        glue = RC * self.glue_per_frame
         self.glue_host = torch.from_numpy(rand_elements(rng, glue, "witness")).pin_memory()
         self.ncols = self.nW + 3
         tail = dev(rand_elements(rng, 3))
@@ -180,7 +185,7 @@ class FoldStepGPU:
         self.z2, self.W2 = [], []
         for _ in range(2):
             z = torch.empty(self.ncols * 32, dtype=torch.uint8, device="cuda")
-            z[self.slot_region * 32:self.nW * 32] = self.glue_host.cuda()
+            z[:self.nW * 32].view(RC, AUX_PER_FRAME * 32)[:, self.slot_per_frame * 32:] = self.glue_host.cuda().view(RC, -1)
             z[self.nW * 32:] = tail
             self.z2.append(z)
             self.W2.append(z[:self.nW * 32])
@@ -204,8 +209,8 @@ class FoldStepGPU:
         t = self.torch
         self.pipe = NovaFoldPipeline(t, FIELD, CURVE, self.ck, self.nW, self.nT, [(rp, col, val) for rp, col, val, _ in self.mats],
                                      self.u1, self.u2, self.z1, self.E1, self.z2, world=self.world)
-        self.slot_batches = [SlotBatch(a, n, off, self.slot_pre_dev[a]) for a, n, off, _blk in self.slot_layout]
-        self.slot_batches.append(SlotBatch(0, self.bd_n, self.bd_off, self.bd_dev))
+        self.slot_batches = [SlotBatch(a, n, 0, self.slot_pre_dev[a], d_offsets=offs) for a, n, offs, _blk in self.slot_layout]
+        self.slot_batches.append(SlotBatch(0, self.bd_n, 0, self.bd_dev, d_offsets=self.bd_offs))
         self.sS = t.cuda.Stream()                          # secondary-circuit commitments
         self.ck2b = self.ck2.clone()
         self.prefetched = None                             # step index whose stage A is in flight
@@ -216,7 +221,8 @@ class FoldStepGPU:
         for arity, h in self.slot_pre_host.items():
             self.slot_pre_dev[arity].copy_(h, non_blocking=True)
         self.bd_dev.copy_(self.bd_host, non_blocking=True)
-        self.W2[b][self.slot_region * 32:].copy_(self.glue_host, non_blocking=True)
+        # LEM-body aux of every frame (strided 2-D copy: 1311 elements after each frame's 7808 slot elements)
+        self.W2[b].view(RC, AUX_PER_FRAME * 32)[:, self.slot_per_frame * 32:].copy_(self.glue_host.view(RC, -1), non_blocking=True)
 
     @staticmethod
     def challenge(cw, ct):

@@ -89,6 +89,13 @@ int lurk_poseidon_witness_batch(int field_id, int arity, const uint8_t *preimage
                                 int fmt);
 int lurk_poseidon_witness_batch_dev(int field_id, int arity, const void *d_preimages, size_t n, void *d_blocks,
                                     int fmt, void *stream);
+/* In-place form for the step witness: block k is written at element offset d_offsets[k] (u64, device) of d_base.  In the
+ * reference every frame's aux is [its slot blocks in slot order | LEM body aux] (synthesize_frames_parallel,
+ * src/lem/multiframe.rs:635-712), so the blocks of one slot type are strided by the frame length (9119 on BN256). */
+int lurk_poseidon_witness_scatter_dev(int field_id, int arity, const void *d_preimages, size_t n, void *d_base,
+                                      const void *d_offsets, int fmt, void *stream);
+int lurk_bitdecomp_witness_scatter_dev(int field_id, const void *d_values, size_t n, void *d_base, const void *d_offsets,
+                                       int fmt, void *stream);
 size_t lurk_bitdecomp_witness_block(int field_id);
 int lurk_bitdecomp_witness_batch(int field_id, const uint8_t *values, size_t n, uint8_t *blocks, int fmt);
 int lurk_bitdecomp_witness_batch_dev(int field_id, const void *d_values, size_t n, void *d_blocks, int fmt,

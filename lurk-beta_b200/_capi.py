@@ -36,6 +36,8 @@ PROTOTYPES = {
     "lurk_poseidon_witness_block": (_sz, [_i, _i]),
     "lurk_poseidon_witness_batch": (_i, [_i, _i, _vp, _sz, _vp, _i]),
     "lurk_poseidon_witness_batch_dev": (_i, [_i, _i, _vp, _sz, _vp, _i, _vp]),
+    "lurk_poseidon_witness_scatter_dev": (_i, [_i, _i, _vp, _sz, _vp, _vp, _i, _vp]),
+    "lurk_bitdecomp_witness_scatter_dev": (_i, [_i, _vp, _sz, _vp, _vp, _i, _vp]),
     "lurk_bitdecomp_witness_block": (_sz, [_i]),
     "lurk_bitdecomp_witness_batch": (_i, [_i, _vp, _sz, _vp, _i]),
     "lurk_bitdecomp_witness_batch_dev": (_i, [_i, _vp, _sz, _vp, _i, _vp]),

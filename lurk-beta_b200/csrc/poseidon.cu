@@ -218,6 +218,29 @@ int lurk_poseidon_witness_batch_dev(int field_id, int arity, const void *d_preim
     });
 }
 
+int lurk_poseidon_witness_scatter_dev(int field_id, int arity, const void *d_preimages, size_t n, void *d_base, const void *d_offsets,
+                                      int fmt, void *stream) {
+    if (!fmt_ok(fmt)) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
+    if (n && !d_offsets) { set_error("null offsets"); return LURK_ERR_ARG; }
+    LURK_TRY(require_gpu());
+    return dispatch_field(field_id, [&](auto f) {
+        using F = decltype(f);
+        return launch_poseidon<F, true>(arity, d_preimages, n, d_base, fmt, fmt, (cudaStream_t)stream, (const uint64_t *)d_offsets);
+    });
+}
+int lurk_bitdecomp_witness_scatter_dev(int field_id, const void *d_values, size_t n, void *d_base, const void *d_offsets, int fmt,
+                                       void *stream) {
+    if (!fmt_ok(fmt)) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
+    if (n && !d_offsets) { set_error("null offsets"); return LURK_ERR_ARG; }
+    LURK_TRY(require_gpu());
+    if (n == 0) return LURK_OK;
+    int blk = (int)lurk_bitdecomp_witness_block(field_id);
+    return dispatch_field(field_id, [&](auto f) {
+        using F = decltype(f);
+        return launch_bitdecomp<F>(d_values, n, d_base, blk, fmt, (cudaStream_t)stream, (const uint64_t *)d_offsets);
+    });
+}
+
 size_t lurk_bitdecomp_witness_block(int field_id) {
     size_t out = 0;
     dispatch_field(field_id, [&](auto f) {

@@ -120,7 +120,7 @@ __device__ __forceinline__ void matvec(const SpongeState<F> &S, const F *M, int 
 template <class F, int ARITY, bool WITNESS>
 __global__ void __launch_bounds__(ARITY >= 6 ? 384 : 512)
 poseidon_kernel(const F *__restrict__ g_consts, PoseidonLayout L, F tag, const F *__restrict__ pre, size_t n,
-                F *__restrict__ out, int in_fmt, int out_fmt) {
+                F *__restrict__ out, const uint64_t *__restrict__ offs, int in_fmt, int out_fmt) {
     constexpr int T = ARITY + 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
@@ -143,7 +143,7 @@ poseidon_kernel(const F *__restrict__ g_consts, PoseidonLayout L, F tag, const F
     const int half = L.rf / 2;
     for (size_t h = (size_t)blockIdx.x * blockDim.x + tid; h < n; h += (size_t)gridDim.x * blockDim.x) {
         const F *p = pre + h * ARITY;
-        F *wout = WITNESS ? out + h * (size_t)L.block_elems : nullptr;
+        F *wout = WITNESS ? out + (offs ? offs[h] : h * (size_t)L.block_elems) : nullptr;
         AuxSink<F, WITNESS> aux;
         aux.next = wout + ARITY;
         aux.fmt = out_fmt;
@@ -233,7 +233,7 @@ __device__ __forceinline__ F shfl_down_fe(const F &x, int d) {
 template <class F, int ARITY, bool WITNESS>
 __global__ void __launch_bounds__(128)
 poseidon_warp_kernel(const F *__restrict__ g_consts, PoseidonLayout L, F tag, const F *__restrict__ pre, size_t n,
-                     F *__restrict__ out, int in_fmt, int out_fmt) {
+                     F *__restrict__ out, const uint64_t *__restrict__ offs, int in_fmt, int out_fmt) {
     constexpr int T = ARITY + 1;
     constexpr int GPW = 32 / T;   // sponges per warp
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -257,7 +257,7 @@ poseidon_warp_kernel(const F *__restrict__ g_consts, PoseidonLayout L, F tag, co
     const bool live = g < GPW && h < n;                // idle lanes run the same code on zeros and never store
     const int half = L.rf / 2;
 
-    F *wout = (WITNESS && live) ? out + h * (size_t)L.block_elems : nullptr;
+    F *wout = (WITNESS && live) ? out + (offs ? offs[h] : h * (size_t)L.block_elems) : nullptr;
     const bool mont_out = out_fmt == LURK_FMT_MONTGOMERY;
     // absorb
     F s = tag;
@@ -340,14 +340,14 @@ poseidon_warp_kernel(const F *__restrict__ g_consts, PoseidonLayout L, F tag, co
 // joins the current run; at the first 0 after a run the run (plus the previous run result) is AND-folded, one
 // aux per AND, then the bit is allocated.  Output values are 0/1 field elements.
 template <class F>
-__global__ void bitdecomp_kernel(const F *__restrict__ vals, size_t n, F *__restrict__ out, int block_elems, int in_fmt,
-                                 int out_fmt) {
+__global__ void bitdecomp_kernel(const F *__restrict__ vals, size_t n, F *__restrict__ out, const uint64_t *__restrict__ offs,
+                                 int block_elems, int in_fmt, int out_fmt) {
     using P = typename F::Params;
     size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= n) return;
     F raw = load_fe<F>(vals + h);
     F x = in_fmt == LURK_FMT_MONTGOMERY ? raw.to_canonical() : raw;
-    F *o = out + h * (size_t)block_elems;
+    F *o = out + (offs ? offs[h] : h * (size_t)block_elems);
     const F one = out_fmt == LURK_FMT_MONTGOMERY ? F::one() : F::from_u64(1).to_canonical();
     const F zero = F::zero();
     store_fe(o, out_fmt == LURK_FMT_MONTGOMERY ? (in_fmt == LURK_FMT_MONTGOMERY ? raw : F::from_canonical(raw)) : x);
@@ -433,8 +433,8 @@ static int device_consts(PoseidonInstance<F> &inst, const F **out) {
 }
 
 template <class F, int ARITY, bool WITNESS>
-static int launch_one(const F *d_consts, const PoseidonInstance<F> &inst, const void *d_pre, size_t n, void *d_out, int in_fmt,
-                      int out_fmt, int grid, int block, cudaStream_t s) {
+static int launch_one(const F *d_consts, const PoseidonInstance<F> &inst, const void *d_pre, size_t n, void *d_out,
+                      const uint64_t *d_offs, int in_fmt, int out_fmt, int grid, int block, cudaStream_t s) {
     constexpr int T = ARITY + 1;
     constexpr int BIG = ARITY >= 6 ? 384 : 512;
     auto kern = poseidon_kernel<F, ARITY, WITNESS>;
@@ -448,13 +448,13 @@ static int launch_one(const F *d_consts, const PoseidonInstance<F> &inst, const 
     });
     LURK_CUDA_TRY(attr_err);
     size_t smem = (size_t)inst.layout.flat_len * sizeof(F) + (size_t)T * 2 * block * sizeof(uint4);
-    kern<<<grid, block, smem, s>>>(d_consts, inst.layout, inst.params.domain_tag, (const F *)d_pre, n, (F *)d_out, in_fmt, out_fmt);
+    kern<<<grid, block, smem, s>>>(d_consts, inst.layout, inst.params.domain_tag, (const F *)d_pre, n, (F *)d_out, d_offs, in_fmt, out_fmt);
     LURK_CUDA_TRY(cudaGetLastError());
     return LURK_OK;
 }
 
 template <class F, int ARITY, bool WITNESS>
-static int launch_arity(const void *d_pre, size_t n, void *d_out, int in_fmt, int out_fmt, cudaStream_t s) {
+static int launch_arity(const void *d_pre, size_t n, void *d_out, const uint64_t *d_offs, int in_fmt, int out_fmt, cudaStream_t s) {
     if (n == 0) return LURK_OK;
     PoseidonInstance<F> &inst = instance<F>(ARITY);
     const F *d_consts = nullptr;
@@ -463,7 +463,7 @@ static int launch_arity(const void *d_pre, size_t n, void *d_out, int in_fmt, in
     constexpr int BIG = ARITY >= 6 ? 384 : 512;
     if (n >= (size_t)sms * BIG / 2) {
         // throughput shape: one persistent CTA per SM
-        return launch_one<F, ARITY, WITNESS>(d_consts, inst, d_pre, n, d_out, in_fmt, out_fmt, sms, BIG, s);
+        return launch_one<F, ARITY, WITNESS>(d_consts, inst, d_pre, n, d_out, d_offs, in_fmt, out_fmt, sms, BIG, s);
     }
     if (n <= 8192) {
         // latency shape (the slot batches of one fold, one level of the store DAG): warp-per-sponge kernel
@@ -478,22 +478,22 @@ static int launch_arity(const void *d_pre, size_t n, void *d_out, int in_fmt, in
         cudaError_t attr_err = cudaSuccess;
         std::call_once(once[dev & 15], [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
         LURK_CUDA_TRY(attr_err);
-        kern<<<grid, 128, smem, s>>>(d_consts, inst.layout, inst.params.domain_tag, (const F *)d_pre, n, (F *)d_out, in_fmt, out_fmt);
+        kern<<<grid, 128, smem, s>>>(d_consts, inst.layout, inst.params.domain_tag, (const F *)d_pre, n, (F *)d_out, d_offs, in_fmt, out_fmt);
         LURK_CUDA_TRY(cudaGetLastError());
         return LURK_OK;
     }
     // medium batches: thread-per-sponge, single warps spread over the SMs
     int grid = (int)((n + 31) / 32);
-    return launch_one<F, ARITY, WITNESS>(d_consts, inst, d_pre, n, d_out, in_fmt, out_fmt, grid, 32, s);
+    return launch_one<F, ARITY, WITNESS>(d_consts, inst, d_pre, n, d_out, d_offs, in_fmt, out_fmt, grid, 32, s);
 }
 
 template <class F, bool WITNESS>
-int launch_poseidon(int arity, const void *d_pre, size_t n, void *d_out, int in_fmt, int out_fmt, cudaStream_t s) {
+int launch_poseidon(int arity, const void *d_pre, size_t n, void *d_out, int in_fmt, int out_fmt, cudaStream_t s, const uint64_t *d_offs) {
     switch (arity) {
-        case 3: return launch_arity<F, 3, WITNESS>(d_pre, n, d_out, in_fmt, out_fmt, s);
-        case 4: return launch_arity<F, 4, WITNESS>(d_pre, n, d_out, in_fmt, out_fmt, s);
-        case 6: return launch_arity<F, 6, WITNESS>(d_pre, n, d_out, in_fmt, out_fmt, s);
-        case 8: return launch_arity<F, 8, WITNESS>(d_pre, n, d_out, in_fmt, out_fmt, s);
+        case 3: return launch_arity<F, 3, WITNESS>(d_pre, n, d_out, d_offs, in_fmt, out_fmt, s);
+        case 4: return launch_arity<F, 4, WITNESS>(d_pre, n, d_out, d_offs, in_fmt, out_fmt, s);
+        case 6: return launch_arity<F, 6, WITNESS>(d_pre, n, d_out, d_offs, in_fmt, out_fmt, s);
+        case 8: return launch_arity<F, 8, WITNESS>(d_pre, n, d_out, d_offs, in_fmt, out_fmt, s);
     }
     set_error("unsupported Poseidon arity %d (HashArity is 3, 4, 6 or 8; src/hash.rs:11-29)", arity);
     return LURK_ERR_ARG;
@@ -508,16 +508,16 @@ int poseidon_instance_info(int arity, const PoseidonParams<F> **params, Poseidon
     return LURK_OK;
 }
 template <class F>
-int launch_bitdecomp(const void *d_values, size_t n, void *d_blocks, int blk, int fmt, cudaStream_t s) {
-    bitdecomp_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((const F *)d_values, n, (F *)d_blocks, blk, fmt, fmt);
+int launch_bitdecomp(const void *d_values, size_t n, void *d_blocks, int blk, int fmt, cudaStream_t s, const uint64_t *d_offs) {
+    bitdecomp_kernel<F><<<(unsigned)((n + 127) / 128), 128, 0, s>>>((const F *)d_values, n, (F *)d_blocks, d_offs, blk, fmt, fmt);
     LURK_CUDA_TRY(cudaGetLastError());
     return LURK_OK;
 }
 
 #define LURK_POSEIDON_INSTANTIATE(F)                                                                                  \
-    template int launch_poseidon<F, false>(int, const void *, size_t, void *, int, int, cudaStream_t);                \
-    template int launch_poseidon<F, true>(int, const void *, size_t, void *, int, int, cudaStream_t);                 \
+    template int launch_poseidon<F, false>(int, const void *, size_t, void *, int, int, cudaStream_t, const uint64_t *); \
+    template int launch_poseidon<F, true>(int, const void *, size_t, void *, int, int, cudaStream_t, const uint64_t *);  \
     template int poseidon_instance_info<F>(int, const PoseidonParams<F> **, PoseidonLayout *);                        \
-    template int launch_bitdecomp<F>(const void *, size_t, void *, int, int, cudaStream_t);
+    template int launch_bitdecomp<F>(const void *, size_t, void *, int, int, cudaStream_t, const uint64_t *);
 
 }  // namespace lurk

@@ -27,8 +27,11 @@ from .commit import point_sum
 class SlotBatch:
     """slot preimages of one step for one slot type, and where their witness blocks go inside W"""
 
-    def __init__(self, arity, count, offset_elems, d_preimages):
-        self.arity, self.count, self.offset, self.d_pre = arity, count, offset_elems, d_preimages   # arity 0 = BitDecomp
+    def __init__(self, arity, count, offset_elems, d_preimages, d_offsets=None):
+        """arity 0 = BitDecomp.  Blocks go to W contiguously from `offset_elems`, or -- the reference's real layout, every
+        frame's aux = [its slot blocks | LEM body aux] (src/lem/multiframe.rs:635-712) -- block k to element offset
+        d_offsets[k] (device tensor of u64)."""
+        self.arity, self.count, self.offset, self.d_pre, self.d_offsets = arity, count, offset_elems, d_preimages, d_offsets
 
 
 class NovaFoldPipeline:
@@ -79,11 +82,18 @@ class NovaFoldPipeline:
         for idx, sb in enumerate(slot_batches):
             st = self.sK[idx % len(self.sK)]
             dst = W2.data_ptr() + sb.offset * 32
-            if sb.arity:
-                chk(lib.lurk_poseidon_witness_batch_dev(self.field_id, sb.arity, sb.d_pre.data_ptr(), sb.count, dst, M,
-                                                        C.c_void_p(st.cuda_stream)))
+            cs = C.c_void_p(st.cuda_stream)
+            if sb.d_offsets is not None:
+                if sb.arity:
+                    chk(lib.lurk_poseidon_witness_scatter_dev(self.field_id, sb.arity, sb.d_pre.data_ptr(), sb.count, W2.data_ptr(),
+                                                              sb.d_offsets.data_ptr(), M, cs))
+                else:
+                    chk(lib.lurk_bitdecomp_witness_scatter_dev(self.field_id, sb.d_pre.data_ptr(), sb.count, W2.data_ptr(),
+                                                               sb.d_offsets.data_ptr(), M, cs))
+            elif sb.arity:
+                chk(lib.lurk_poseidon_witness_batch_dev(self.field_id, sb.arity, sb.d_pre.data_ptr(), sb.count, dst, M, cs))
             else:
-                chk(lib.lurk_bitdecomp_witness_batch_dev(self.field_id, sb.d_pre.data_ptr(), sb.count, dst, M, C.c_void_p(st.cuda_stream)))
+                chk(lib.lurk_bitdecomp_witness_batch_dev(self.field_id, sb.d_pre.data_ptr(), sb.count, dst, M, cs))
             k += 1
         evs = []
         for st in self.sK:

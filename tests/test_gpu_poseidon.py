@@ -167,3 +167,34 @@ def test_concurrent_callers(L, oracle):
         pre, got = results[k]
         m = min(n, 3000)
         assert np.array_equal(got[:m * 32], oracle.poseidon_hash_batch(field, arity, pre[:m * arity * 32], nthreads=4))
+
+
+def test_slot_witness_scatter_into_frame_layout(L, oracle):
+    """in-place form: blocks land at caller-given element offsets of the step witness -- the reference's layout is
+    per frame [slot blocks | LEM body aux] (src/lem/multiframe.rs:635-712), 9119 elements per frame on BN256"""
+    import torch
+    lib, chk = L._capi.lib(), L._capi.check
+    field, frames, frame_len = 0, 5, 9119
+    W = torch.full((frames * frame_len * 32,), 0xAB, dtype=torch.uint8, device="cuda")
+    base = 0
+    expected = np.full(frames * frame_len * 32, 0xAB, dtype=np.uint8).reshape(frames, frame_len, 32)
+    for arity, per_frame in ((4, 14), (8, 6), (3, 1)):
+        n = frames * per_frame
+        blk = oracle.witness_block(field, arity)
+        pre = random_elements(field, n * arity, seed=arity, shape="lem")
+        offs = (np.arange(frames, dtype=np.uint64)[:, None] * frame_len + base + np.arange(per_frame, dtype=np.uint64)[None, :] * blk).reshape(-1)
+        d_pre, d_off = torch.from_numpy(pre).cuda(), torch.from_numpy(offs).cuda()
+        chk(lib.lurk_poseidon_witness_scatter_dev(field, arity, d_pre.data_ptr(), n, W.data_ptr(), d_off.data_ptr(), L.FMT_CANONICAL, None))
+        want = oracle.poseidon_witness_batch(field, arity, pre, nthreads=4).reshape(frames, per_frame * blk, 32)
+        expected[:, base:base + per_frame * blk] = want
+        base += per_frame * blk
+    vals = random_elements(field, frames * 3, seed=77, shape="witness")
+    bd = oracle.bitdecomp_size(field)
+    offs = (np.arange(frames, dtype=np.uint64)[:, None] * frame_len + base + np.arange(3, dtype=np.uint64)[None, :] * bd).reshape(-1)
+    d_v, d_off = torch.from_numpy(vals).cuda(), torch.from_numpy(offs).cuda()
+    chk(lib.lurk_bitdecomp_witness_scatter_dev(field, d_v.data_ptr(), frames * 3, W.data_ptr(), d_off.data_ptr(), L.FMT_CANONICAL, None))
+    expected[:, base:base + 3 * bd] = oracle.bitdecomp_witness_batch(field, vals).reshape(frames, 3 * bd, 32)
+    base += 3 * bd
+    assert base == 7808
+    got = W.cpu().numpy().reshape(frames, frame_len, 32)
+    assert np.array_equal(got, expected)           # includes: the 1311 body-aux elements of every frame are untouched
