@@ -45,6 +45,7 @@ BITDECOMP_PER_FRAME = 3
 SECONDARY_N = 10_000          # secondary-circuit witness / constraint count (order of magnitude)
 FIELD, CURVE, CURVE2 = 0, 0, 1   # BN254 Fr; BN254 G1 primary, Grumpkin secondary
 LIVE_SLOT_FRACTION = 0.25     # most slots of a frame are dummies (multiframe.rs:553-577)
+PREFETCH_DEPTH = 1            # stage A (slot witnesses, commit(W), Az2..) runs this many steps ahead of the fold
 
 
 def rand_elements(rng, count, shape="uniform"):
@@ -156,13 +157,13 @@ class FoldStepGPU:
             pre[dummy] = 0
             blk = self.lib.lurk_poseidon_witness_block(FIELD, arity)
             self.slot_pre_host[arity] = torch.from_numpy(pre.reshape(-1)).pin_memory()
-            self.slot_pre_dev[arity] = self.slot_pre_host[arity].cuda()
+            self.slot_pre_dev[arity] = [self.slot_pre_host[arity].cuda() for _ in range(PREFETCH_DEPTH + 1)]   # one per in-flight step
             offs = (np.arange(RC, dtype=np.uint64)[:, None] * AUX_PER_FRAME + frame_off + np.arange(per_frame, dtype=np.uint64)[None, :] * blk).reshape(-1)
             self.slot_layout.append((arity, n, torch.from_numpy(offs).cuda(), blk))
             frame_off += per_frame * blk
         nbd = RC * BITDECOMP_PER_FRAME
         self.bd_host = torch.from_numpy(rand_elements(rng, nbd, "witness")).pin_memory()
-        self.bd_dev = self.bd_host.cuda()
+        self.bd_dev = [self.bd_host.cuda() for _ in range(PREFETCH_DEPTH + 1)]
         self.bd_n = nbd
         offs = (np.arange(RC, dtype=np.uint64)[:, None] * AUX_PER_FRAME + frame_off + np.arange(BITDECOMP_PER_FRAME, dtype=np.uint64)[None, :] * self.bd_block).reshape(-1)
         self.bd_offs = torch.from_numpy(offs).cuda()
@@ -183,7 +184,7 @@ class FoldStepGPU:
         self.z1[self.nW * 32:] = tail
         self.W1 = self.z1[:self.nW * 32]
         self.z2, self.W2 = [], []
-        for _ in range(2):
+        for _ in range(PREFETCH_DEPTH + 1):
             z = torch.empty(self.ncols * 32, dtype=torch.uint8, device="cuda")
             z[:self.nW * 32].view(RC, AUX_PER_FRAME * 32)[:, self.slot_per_frame * 32:] = self.glue_host.cuda().view(RC, -1)
             z[self.nW * 32:] = tail
@@ -209,18 +210,21 @@ class FoldStepGPU:
         t = self.torch
         self.pipe = NovaFoldPipeline(t, FIELD, CURVE, self.ck, self.nW, self.nT, [(rp, col, val) for rp, col, val, _ in self.mats],
                                      self.u1, self.u2, self.z1, self.E1, self.z2, world=self.world)
-        self.slot_batches = [SlotBatch(a, n, 0, self.slot_pre_dev[a], d_offsets=offs) for a, n, offs, _blk in self.slot_layout]
-        self.slot_batches.append(SlotBatch(0, self.bd_n, 0, self.bd_dev, d_offsets=self.bd_offs))
+        self.slot_batches = []
+        for b in range(PREFETCH_DEPTH + 1):
+            sb = [SlotBatch(a, n, 0, self.slot_pre_dev[a][b], d_offsets=offs) for a, n, offs, _blk in self.slot_layout]
+            sb.append(SlotBatch(0, self.bd_n, 0, self.bd_dev[b], d_offsets=self.bd_offs))
+            self.slot_batches.append(sb)
         self.sS = t.cuda.Stream()                          # secondary-circuit commitments
         self.ck2b = self.ck2.clone()
-        self.prefetched = None                             # step index whose stage A is in flight
+        self.prefetched = -1                               # last step index whose stage A has been enqueued
         self.step_index = 0
 
     def stage_inputs(self, b):
         """host -> device copy of one step's inputs from pinned memory (the e2e leg), into buffer b"""
         for arity, h in self.slot_pre_host.items():
-            self.slot_pre_dev[arity].copy_(h, non_blocking=True)
-        self.bd_dev.copy_(self.bd_host, non_blocking=True)
+            self.slot_pre_dev[arity][b].copy_(h, non_blocking=True)
+        self.bd_dev[b].copy_(self.bd_host, non_blocking=True)
         # LEM-body aux of every frame (strided 2-D copy: 1311 elements after each frame's 7808 slot elements)
         self.W2[b].view(RC, AUX_PER_FRAME * 32)[:, self.slot_per_frame * 32:].copy_(self.glue_host.view(RC, -1), non_blocking=True)
 
@@ -238,13 +242,14 @@ class FoldStepGPU:
             self._setup()
         L, M = self.L, self.L.FMT_MONTGOMERY
         i = self.step_index
-        b = i & 1
+        nb = PREFETCH_DEPTH + 1
+        b = i % nb
         before = self.stage_inputs if staged else None
-        if self.prefetched != i:
-            self.pipe.stage_a(b, self.slot_batches, before)
         kA = self.pipe.launches_A
-        self.pipe.stage_a(b ^ 1, self.slot_batches, before)      # prefetch step i+1
-        self.prefetched = i + 1
+        while self.prefetched < i + PREFETCH_DEPTH:              # keep stage A PREFETCH_DEPTH steps ahead
+            self.prefetched += 1
+            self.pipe.stage_a(self.prefetched % nb, self.slot_batches[self.prefetched % nb], before)
+            kA = self.pipe.launches_A
         # secondary circuit (Grumpkin): two small commitments, independent of the primary fold
         self.ck2.launch_device(self.W_sec.data_ptr(), SECONDARY_N, fmt=M, stream=self.sS.cuda_stream)
         self.ck2b.launch_device(self.T_sec.data_ptr(), SECONDARY_N, fmt=M, stream=self.sS.cuda_stream)
@@ -259,9 +264,10 @@ class FoldStepGPU:
 
     def drain(self):
         """collect the commit(W) of a prefetched step that will not be folded (end of a timed region)"""
-        if getattr(self, "prefetched", None) is not None and self.prefetched == self.step_index:
-            self.pipe.drain(self.step_index & 1)
-            self.prefetched = None
+        nb = PREFETCH_DEPTH + 1
+        while getattr(self, "prefetched", -1) >= self.step_index:
+            self.pipe.drain(self.prefetched % nb)
+            self.prefetched -= 1
 
 
 def run_gpu(args):

@@ -73,7 +73,8 @@ static MsmPlan make_plan(size_t n, int scalar_bits, int fixed_c = 0) {
     size_t cap = n * (size_t)p.nwin;
     size_t want_threads = (size_t)sm_count() * 1024;
     size_t seg = (cap + want_threads - 1) / want_threads;
-    p.seg = (uint32_t)std::min<size_t>(32, std::max<size_t>(8, seg));
+    static const size_t seg_cap = [] { const char *e = getenv("LURK_MSM_SEG"); return e ? (size_t)atoi(e) : (size_t)32; }();   // tuning aid
+    p.seg = (uint32_t)std::min<size_t>(seg_cap, std::max<size_t>(8, seg));
     p.t1 = (uint32_t)((cap + p.seg - 1) / p.seg);
     if (p.t1 == 0) p.t1 = 1;
     p.chunk = std::min<uint32_t>(16, p.nb);

@@ -49,16 +49,17 @@ class NovaFoldPipeline:
         self.world, self.group = world, group
         self.T = torch.empty(n_t * 32, dtype=torch.uint8, device="cuda")
         self.mv1 = [torch.empty(n_t * 32, dtype=torch.uint8, device="cuda") for _ in range(3)]
-        self.mv2 = [[torch.empty(n_t * 32, dtype=torch.uint8, device="cuda") for _ in range(3)] for _ in range(2)]
+        nb = len(z2_buffers)                                    # stage A may run nb - 1 steps ahead of stage B
+        self.mv2 = [[torch.empty(n_t * 32, dtype=torch.uint8, device="cuda") for _ in range(3)] for _ in range(nb)]
         self.sK = [torch.cuda.Stream() for _ in range(3)]      # slot-witness kernels (one stream per slot type), commit(W)
         self.sA = torch.cuda.Stream()                          # Az2, Bz2, Cz2 of the prefetched step
         self.sB = torch.cuda.Stream()                          # Az1.., cross term, commit(T), fold
-        self.ckW = [ck, ck.clone()]
+        self.ckW = [ck] + [ck.clone() for _ in range(nb - 1)]
         self.ckT = ck.clone()
         for c in (*self.ckW, self.ckT):
             c.set_profiling(True)
-        self.ev_fold = [None, None]                            # fold that last read W2[b]
-        self.ev_A = [None, None]                               # stage A of buffer b complete (Az2.. ready)
+        self.ev_fold = [None] * nb                             # fold that last read W2[b]
+        self.ev_A = [None] * nb                                # stage A of buffer b complete (Az2.. ready)
         self.accumulate_ms = []                                # device time of the dominant kernel, per commitment
         self.launches_A = self.launches_B = 0
 
