@@ -1,632 +1,15 @@
-// K4: Pedersen commitment = Pippenger multi-scalar multiplication on sm_100a.
-//
-// Replaces Arecibo's CommitmentEngineTrait::commit -> DlogGroup::vartime_multiscalar_mul (third-party crate, called
-// from RecursiveSNARK::prove_step; reference call sites src/proof/nova.rs:287,292, src/proof/supernova.rs:231-244).
-// The commitment key is fixed per (rc, Lang) (src/proof/nova.rs:196-216), so it is uploaded once into a context and
-// kept in HBM in Montgomery affine form (64 B / point); every call streams 32 B scalars.
-//
-// Pipeline (all on one stream, no host synchronisation before the final 2 KB read-back; launch and finish are
-// separate entry points so that independent commitments overlap):
-//   1. digits+histogram: one thread per scalar; signed c-bit windows (buckets 1..2^(c-1), sign folded into the point);
-//      warp-aggregated atomics (__match_any_sync) so the 0/1-heavy witness vectors do not serialise on
-//      one counter.
-//   2. exclusive scan of the (windows x 2^(c-1)) bucket counts.
-//   3. scatter: point index | sign written at its bucket's next slot (counting sort; order inside a bucket is free
-//      because point addition commutes -- the affine result is canonical).
-//   4. bucket accumulation, the hot kernel: the sorted list is cut into fixed-length segments, one per thread,
-//      independent of the bucket sizes (perfect balance for any scalar distribution).  A thread gathers its bases
-//      with 128-bit loads (next point prefetched during the current addition), adds them in XYZZ coordinates
-//      (8M+2S mixed addition, no inversions) and flushes a bucket sum whenever the bucket id changes.  The first run
-//      of a segment may continue a bucket started by the previous thread: it goes to a (key, point) partial list
-//      which is reduced by the same rule in a few geometrically shrinking passes.
-//   5. per-window running-sum reduction (chunks of buckets in parallel, then one CTA per window).
-//   6. host: Horner combine of the <= 64 window sums and one inversion to affine.
-// Integer-ALU bound: ~10 Montgomery products per (scalar, window); algorithmic traffic 96 B per term.
-#include "common.cuh"
-
-#include <algorithm>
-#include <atomic>
-#include <mutex>
-#include <thread>
+// C-ABI front end of the Pedersen commitment (S4 in include/lurk_b200.h); the kernels and the per-curve pipeline are in
+// msm_impl.cuh and are compiled once per curve in msm_inst.cu.
+#include "msm_impl.cuh"
 
 namespace lurk {
-
-static constexpr uint32_t KEY_NONE = 0xffffffffu;
-
-struct MsmPlan {
-    int c = 0;             // window bits
-    int nwin = 0;          // windows
-    uint32_t nb = 0;       // buckets per window = 2^(c-1)
-    uint32_t total_buckets = 0;
-    uint32_t seg = 0;      // sorted entries per level-1 thread
-    uint32_t t1 = 0;       // level-1 threads = partial slots
-    uint32_t chunk = 0;    // buckets per bucket-reduce thread
-    // fixed-base mode (window multiples of every base precomputed): one shared bucket set of 2^(c-1) buckets, cut into
-    // `vwin` virtual windows of `nb` buckets for the reduction; entries address table[w * key_n + i]
-    bool fixed = false;
-    uint32_t vwin = 0;
-};
-
-static int fixed_base_window(size_t key_n) {
-    int lg = 0;
-    while (((size_t)1 << (lg + 1)) <= key_n) lg++;
-    return std::min(20, std::max(10, lg - 1));
-}
-
-static MsmPlan make_plan(size_t n, int scalar_bits, int fixed_c = 0) {
-    MsmPlan p;
-    int lg = 0;
-    while (((size_t)1 << (lg + 1)) <= n) lg++;
-    p.c = fixed_c ? fixed_c : std::min(20, std::max(4, lg - 5));
-    p.nwin = scalar_bits / p.c + 1;
-    if (fixed_c) {
-        p.fixed = true;
-        const uint32_t all = 1u << (p.c - 1);
-        p.nb = std::min<uint32_t>(all, 1u << 15);
-        p.vwin = all / p.nb;
-        p.total_buckets = all;
-    } else {
-        p.nb = 1u << (p.c - 1);
-        p.vwin = (uint32_t)p.nwin;
-        p.total_buckets = p.nb * (uint32_t)p.nwin;
-    }
-    size_t cap = n * (size_t)p.nwin;
-    size_t want_threads = (size_t)sm_count() * 1024;
-    size_t seg = (cap + want_threads - 1) / want_threads;
-    static const size_t seg_cap = [] { const char *e = getenv("LURK_MSM_SEG"); return e ? (size_t)atoi(e) : (size_t)32; }();   // tuning aid
-    p.seg = (uint32_t)std::min<size_t>(seg_cap, std::max<size_t>(8, seg));
-    p.t1 = (uint32_t)((cap + p.seg - 1) / p.seg);
-    if (p.t1 == 0) p.t1 = 1;
-    p.chunk = std::min<uint32_t>(16, p.nb);
-    return p;
-}
-
-// ----------------------------------------------------------------------------- kernels
-// unsigned c-bit window starting at `bit` of a 256-bit little-endian integer
-__device__ __forceinline__ uint32_t window_bits(const uint32_t k[8], int bit, int c) {
-    int word = bit >> 5, sh = bit & 31;
-    if (word >= 8) return 0;
-    uint32_t lo = k[word] >> sh;
-    if (sh + c > 32 && word + 1 < 8) lo |= k[word + 1] << (32 - sh);
-    return lo & ((1u << c) - 1);
-}
-
-template <class Fs>
-__global__ void __launch_bounds__(256) msm_count_kernel(const Fs *__restrict__ scalars, size_t n, int fmt, int c, int nwin, uint32_t key_stride,
-                                                        uint32_t *__restrict__ counts) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;
-    // all lanes walk the windows together so the warp-aggregation below sees converged lanes
-    Fs k = Fs::zero();
-    if (live) { k = load_fe<Fs>(scalars + i); if (fmt == LURK_FMT_MONTGOMERY) k = k.to_canonical(); }
-    uint32_t carry = 0;
-    const uint32_t half = 1u << (c - 1);
-    const uint32_t lane = threadIdx.x & 31;
-    for (int w = 0; w < nwin; w++) {
-        uint32_t raw = window_bits(k.v, w * c, c) + carry;
-        uint32_t neg = raw > half;
-        uint32_t mag = neg ? (1u << c) - raw : raw;
-        carry = neg;
-        uint32_t key = (live && mag) ? (uint32_t)w * key_stride + (mag - 1) : KEY_NONE;
-        uint32_t peers = __match_any_sync(0xffffffffu, key);
-        if (key != KEY_NONE && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(counts + key, (uint32_t)__popc(peers));
-    }
-}
-
-// ---- exclusive scan of the bucket counts: offsets[0..len], offsets[len] = total.
-// Three small launches: per-CTA sums of 4096 counts, one CTA scanning the <= 2048 CTA sums, per-CTA scan with carry-in.
-static constexpr uint32_t SCAN_TILE = 4096;
-
-__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t sum, uint32_t *total) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    uint32_t incl = sum;
-    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
-    if (lane == 31) warp_sums[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        uint32_t ws = warp_sums[lane], wi = ws;
-        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= (uint32_t)d) wi += t; }
-        warp_sums[lane] = wi - ws;
-        if (lane == 31) carry_s = wi;
-    }
-    __syncthreads();
-    if (total) *total = carry_s;
-    return warp_sums[wid] + incl - sum;
-}
-
-__global__ void __launch_bounds__(1024) msm_scan_tile_sums_kernel(const uint32_t *__restrict__ counts, uint32_t len, uint32_t *__restrict__ tile_sums) {
-    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
-    uint32_t sum = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) if (base + k < len) sum += counts[base + k];
-    uint32_t total;
-    block_exclusive_scan_1024(sum, &total);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-// one CTA: tile_offsets[0..ntiles] from tile_sums (ntiles <= 4096)
-__global__ void __launch_bounds__(1024) msm_scan_tiles_kernel(const uint32_t *__restrict__ tile_sums, uint32_t ntiles, uint32_t *__restrict__ tile_offsets) {
-    const uint32_t base = threadIdx.x * 4;
-    uint32_t v[4], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) { v[k] = base + k < ntiles ? tile_sums[base + k] : 0; sum += v[k]; }
-    uint32_t total;
-    uint32_t run = block_exclusive_scan_1024(sum, &total);
-#pragma unroll
-    for (int k = 0; k < 4; k++) { if (base + k < ntiles) tile_offsets[base + k] = run; run += v[k]; }
-    if (threadIdx.x == 0) tile_offsets[ntiles] = total;
-}
-__global__ void __launch_bounds__(1024) msm_scan_apply_kernel(const uint32_t *__restrict__ counts, uint32_t len, const uint32_t *__restrict__ tile_offsets,
-                                                              uint32_t ntiles, uint32_t *__restrict__ offsets) {
-    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
-    uint32_t v[4], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) { v[k] = base + k < len ? counts[base + k] : 0; sum += v[k]; }
-    uint32_t run = tile_offsets[blockIdx.x] + block_exclusive_scan_1024(sum, nullptr);
-#pragma unroll
-    for (int k = 0; k < 4; k++) { if (base + k < len) offsets[base + k] = run; run += v[k]; }
-    if (blockIdx.x == 0 && threadIdx.x == 0) offsets[len] = tile_offsets[ntiles];
-}
-
-template <class Fs>
-__global__ void __launch_bounds__(256) msm_scatter_kernel(const Fs *__restrict__ scalars, size_t n, int fmt, int c, int nwin, uint32_t key_stride,
-                                                          uint32_t base_stride, const uint32_t *__restrict__ offsets,
-                                                          uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;
-    Fs k = Fs::zero();
-    if (live) { k = load_fe<Fs>(scalars + i); if (fmt == LURK_FMT_MONTGOMERY) k = k.to_canonical(); }
-    uint32_t carry = 0;
-    const uint32_t half = 1u << (c - 1);
-    const uint32_t lane = threadIdx.x & 31;
-    for (int w = 0; w < nwin; w++) {
-        uint32_t raw = window_bits(k.v, w * c, c) + carry;
-        uint32_t neg = raw > half;
-        uint32_t mag = neg ? (1u << c) - raw : raw;
-        carry = neg;
-        uint32_t key = (live && mag) ? (uint32_t)w * key_stride + (mag - 1) : KEY_NONE;
-        uint32_t peers = __match_any_sync(0xffffffffu, key);
-        uint32_t leader = (uint32_t)(__ffs(peers) - 1);
-        uint32_t base = 0;
-        if (key != KEY_NONE && lane == leader) base = atomicAdd(cursor + key, (uint32_t)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (key != KEY_NONE) {
-            uint32_t rank = __popc(peers & ((1u << lane) - 1));
-            sorted[offsets[key] + base + rank] = ((uint32_t)i + (uint32_t)w * base_stride) | (neg << 31);
-        }
-    }
-}
-
-template <class Fb>
-__device__ __forceinline__ Affine<Fb> load_affine(const Affine<Fb> *p) {
-    Affine<Fb> a;
-    a.x = load_fe<Fb>(&p->x);
-    a.y = load_fe<Fb>(&p->y);
-    return a;
-}
-template <class Fb>
-__device__ __forceinline__ XYZZ<Fb> load_xyzz(const XYZZ<Fb> *p) {
-    XYZZ<Fb> a;
-    a.x = load_fe<Fb>(&p->x); a.y = load_fe<Fb>(&p->y); a.zz = load_fe<Fb>(&p->zz); a.zzz = load_fe<Fb>(&p->zzz);
-    return a;
-}
-template <class Fb>
-__device__ __forceinline__ void store_xyzz(XYZZ<Fb> *p, const XYZZ<Fb> &a) {
-    store_fe(&p->x, a.x); store_fe(&p->y, a.y); store_fe(&p->zz, a.zz); store_fe(&p->zzz, a.zzz);
-}
-
-// level 1: fixed-length segments of the sorted list
-// MINB = resident CTAs per SM the register allocation is held to: 4 (126 registers, no spills) is best while the key is
-// L2 resident; the fixed-base table (1.7 GB, DRAM gathers) gains ~5 % from 5 CTAs (96 registers, ~150 B of spills).
-template <class Fb, int MINB>
-__global__ void __launch_bounds__(128, MINB) msm_accumulate_kernel(const uint32_t *__restrict__ offsets, uint32_t nbuckets,
-                                                             const uint32_t *__restrict__ sorted, const Affine<Fb> *__restrict__ bases,
-                                                             XYZZ<Fb> *__restrict__ bucket_acc, uint32_t *__restrict__ pkey,
-                                                             XYZZ<Fb> *__restrict__ ppt, uint32_t seg, uint32_t nthreads) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nthreads) return;
-    const uint32_t total = offsets[nbuckets];
-    const uint64_t start64 = (uint64_t)t * seg;
-    if (start64 >= total) { pkey[t] = KEY_NONE; return; }
-    const uint32_t start = (uint32_t)start64;
-    const uint32_t end = (uint32_t)min((uint64_t)total, start64 + seg);
-    // bucket containing `start`: largest key with offsets[key] <= start
-    uint32_t lo = 0, hi = nbuckets;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (offsets[mid] <= start) lo = mid; else hi = mid;
-    }
-    uint32_t key = lo;
-    uint32_t run_end = min(offsets[key + 1], end);
-    bool first_run = true;
-    uint32_t e_next = sorted[start];
-    Affine<Fb> p_next = load_affine(bases + (e_next & 0x7fffffffu));
-    XYZZ<Fb> acc = XYZZ<Fb>::identity();
-    // ONE flat loop over the segment: every lane performs exactly one addition per iteration, so lanes whose bucket
-    // boundaries fall at different positions stay converged (a nested per-run loop makes each lane wait for the
-    // longest run in the warp -- measured ~2x on the IMAD pipe).  Flushing a finished run is a short predicated tail.
-    for (uint32_t pos = start; pos < end;) {
-        const uint32_t e = e_next;
-        const Affine<Fb> p = p_next;
-        pos++;
-        if (pos < end) {   // prefetch the next entry while this addition runs
-            e_next = sorted[pos];
-            p_next = load_affine(bases + (e_next & 0x7fffffffu));
-        }
-        acc.add_affine(p, (e >> 31) != 0);
-        if (pos == run_end) {
-            if (first_run) { pkey[t] = key; store_xyzz(ppt + t, acc); first_run = false; }
-            else store_xyzz(bucket_acc + key, acc);   // this run starts exactly at the bucket start: sole initialiser
-            acc = XYZZ<Fb>::identity();
-            if (pos < end) {
-                key++;
-                while (offsets[key + 1] <= pos) key++;   // skip empty buckets
-                run_end = min(offsets[key + 1], end);
-            }
-        }
-    }
-}
-
-// levels >= 2: the same rule on (key, point) lists; keys are non-decreasing, KEY_NONE only as a tail
-template <class Fb>
-__global__ void __launch_bounds__(128) msm_partial_kernel(const uint32_t *__restrict__ keys_in, const XYZZ<Fb> *__restrict__ pts_in,
-                                                          uint32_t count, XYZZ<Fb> *__restrict__ bucket_acc, uint32_t *__restrict__ keys_out,
-                                                          XYZZ<Fb> *__restrict__ pts_out, uint32_t seg, int last_level) {
-    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t s64 = (uint64_t)u * seg;
-    if (s64 >= count) return;
-    const uint32_t s = (uint32_t)s64, e = (uint32_t)min((uint64_t)count, s64 + seg);
-    uint32_t cur = KEY_NONE;
-    bool first_run = true, wrote_out = false;
-    XYZZ<Fb> acc = XYZZ<Fb>::identity();
-    for (uint32_t i = s; i <= e; i++) {
-        const uint32_t k = i < e ? keys_in[i] : KEY_NONE;   // one extra step flushes the last run
-        if (k == cur && k != KEY_NONE) { acc.add(load_xyzz(pts_in + i)); continue; }
-        if (cur != KEY_NONE) {
-            if (first_run && !last_level) { keys_out[u] = cur; store_xyzz(pts_out + u, acc); wrote_out = true; }
-            else { XYZZ<Fb> b = load_xyzz(bucket_acc + cur); b.add(acc); store_xyzz(bucket_acc + cur, b); }
-            first_run = false;
-        }
-        if (k == KEY_NONE) break;
-        cur = k;
-        acc = load_xyzz(pts_in + i);
-    }
-    if (!wrote_out && !last_level) keys_out[u] = KEY_NONE;
-}
-
-template <class Fb>
-__device__ __forceinline__ XYZZ<Fb> shfl_up_xyzz(const XYZZ<Fb> &p, int d) {
-    XYZZ<Fb> r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        r.x.v[i] = __shfl_up_sync(0xffffffffu, p.x.v[i], d);
-        r.y.v[i] = __shfl_up_sync(0xffffffffu, p.y.v[i], d);
-        r.zz.v[i] = __shfl_up_sync(0xffffffffu, p.zz.v[i], d);
-        r.zzz.v[i] = __shfl_up_sync(0xffffffffu, p.zzz.v[i], d);
-    }
-    return r;
-}
-
-// Later levels are latency-bound (few entries): one warp takes 32 consecutive (key, point) entries and combines equal
-// keys with a segmented Hillis-Steele scan over shuffles -- 5 dependent additions per 32x shrink instead of 32.
-template <class Fb>
-__global__ void __launch_bounds__(128) msm_partial_warp_kernel(const uint32_t *__restrict__ keys_in, const XYZZ<Fb> *__restrict__ pts_in,
-                                                               uint32_t count, XYZZ<Fb> *__restrict__ bucket_acc, uint32_t *__restrict__ keys_out,
-                                                               XYZZ<Fb> *__restrict__ pts_out, int last_level) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if ((uint64_t)gw * 32 >= count) return;   // whole warp out of range
-    const uint32_t i = gw * 32 + lane;
-    const uint32_t key = i < count ? keys_in[i] : KEY_NONE;
-    XYZZ<Fb> pt = XYZZ<Fb>::identity();
-    if (key != KEY_NONE) pt = load_xyzz(pts_in + i);
-#pragma unroll 1
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t k2 = __shfl_up_sync(0xffffffffu, key, d);
-        const XYZZ<Fb> p2 = shfl_up_xyzz(pt, d);
-        if (lane >= (uint32_t)d && k2 == key && key != KEY_NONE) pt.add(p2);
-    }
-    const uint32_t first_key = __shfl_sync(0xffffffffu, key, 0);
-    const uint32_t next_key = __shfl_down_sync(0xffffffffu, key, 1);
-    const bool run_end = key != KEY_NONE && (lane == 31 || next_key != key);
-    if (run_end) {
-        if (key == first_key && !last_level) { keys_out[gw] = key; store_xyzz(pts_out + gw, pt); }
-        else { XYZZ<Fb> b = load_xyzz(bucket_acc + key); b.add(pt); store_xyzz(bucket_acc + key, b); }
-    }
-    if (first_key == KEY_NONE && lane == 0 && !last_level) keys_out[gw] = KEY_NONE;
-}
-
-// per chunk of `chunk` buckets [b0, b0+chunk) of window w:  sum_b (b+1) B_b = tri + b0 * S
-template <class Fb>
-__global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(const XYZZ<Fb> *__restrict__ bucket_acc, uint32_t nb, uint32_t chunk,
-                                                                uint32_t nchunks_total, XYZZ<Fb> *__restrict__ chunk_out,
-                                                                XYZZ<Fb> *__restrict__ chunk_sum_out) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nchunks_total) return;
-    const uint32_t per_win = nb / chunk;
-    const uint32_t w = g / per_win, ch = g % per_win;
-    const uint32_t b0 = ch * chunk;
-    const XYZZ<Fb> *B = bucket_acc + (size_t)w * nb + b0;
-    XYZZ<Fb> run = XYZZ<Fb>::identity(), tri = XYZZ<Fb>::identity();
-    for (int b = (int)chunk - 1; b >= 0; b--) {
-        run.add(load_xyzz(B + b));
-        tri.add(run);
-    }
-    if (b0) tri.add(run.mul_u32(b0));
-    store_xyzz(chunk_out + g, tri);
-    if (chunk_sum_out) store_xyzz(chunk_sum_out + g, run);   // plain sum of the chunk (fixed-base mode)
-}
-
-// one CTA per window: sum of its chunk results
-template <class Fb>
-__global__ void __launch_bounds__(256) msm_window_sum_kernel(const XYZZ<Fb> *__restrict__ chunk_in, uint32_t per_win, XYZZ<Fb> *__restrict__ win_out) {
-    __shared__ XYZZ<Fb> sm[256];
-    const uint32_t w = blockIdx.x, tid = threadIdx.x;
-    XYZZ<Fb> acc = XYZZ<Fb>::identity();
-    for (uint32_t i = tid; i < per_win; i += blockDim.x) acc.add(load_xyzz(chunk_in + (size_t)w * per_win + i));
-    sm[tid] = acc;
-    __syncthreads();
-    for (uint32_t stride = blockDim.x / 2; stride > 0; stride >>= 1) {
-        if (tid < stride) { XYZZ<Fb> a = sm[tid]; a.add(sm[tid + stride]); sm[tid] = a; }
-        __syncthreads();
-    }
-    if (tid == 0) store_xyzz(win_out + w, sm[0]);
-}
-
-// Fixed-base table: table[w * n + i] = 2^(c w) * bases[i], affine.  One thread per base walks the windows with c
-// doublings each (XYZZ), then normalises its nwin points with one inversion (Montgomery's trick on the ZZZ coordinates).
-static constexpr int MSM_MAX_TABLE_WINDOWS = 26;
-template <class Fb>
-__global__ void __launch_bounds__(128) msm_precompute_kernel(const Affine<Fb> *__restrict__ bases, size_t n, int c, int nwin,
-                                                             Affine<Fb> *__restrict__ table) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const Affine<Fb> p0 = load_affine(bases + i);
-    XYZZ<Fb> pts[MSM_MAX_TABLE_WINDOWS];
-    Fb pref[MSM_MAX_TABLE_WINDOWS];
-    XYZZ<Fb> cur = XYZZ<Fb>::from_affine(p0);
-    Fb run = Fb::one();
-    for (int w = 0; w < nwin; w++) {
-        if (w) for (int d = 0; d < c; d++) cur = cur.dbl();
-        pts[w] = cur;
-        pref[w] = run;
-        if (!cur.is_identity()) run = run * cur.zzz;
-    }
-    Fb inv = run.inv();
-    for (int w = nwin - 1; w >= 0; w--) {
-        Affine<Fb> a;
-        a.x = Fb::zero();
-        a.y = Fb::zero();
-        if (!pts[w].is_identity()) {
-            const Fb zi = inv * pref[w];            // 1 / ZZZ_w
-            inv = inv * pts[w].zzz;
-            const Fb zz_inv = (zi * pts[w].zz).sqr();
-            a.x = pts[w].x * zz_inv;
-            a.y = pts[w].y * zi;
-        }
-        store_fe(&table[(size_t)w * n + i].x, a.x);
-        store_fe(&table[(size_t)w * n + i].y, a.y);
-    }
-}
-
-// affine bases: canonical -> Montgomery in place
-template <class Fb>
-__global__ void __launch_bounds__(256) msm_bases_to_mont_kernel(Fb *coords, size_t count) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
-        store_fe(coords + i, Fb::from_canonical(load_fe<Fb>(coords + i)));
-}
-
-// ----------------------------------------------------------------------------- context
-struct MsmScratch {
-    DevBuf counts, offsets, tiles, sorted, buckets, pkey[2], ppt[2], chunks, chunk_sums, wins, scalars;
-    void *h_wins = nullptr;   // pinned
-    void *h_stage[2] = {nullptr, nullptr};          // pinned staging for host-buffer scalars
-    cudaEvent_t stage_done[2] = {nullptr, nullptr};
-    ~MsmScratch() {
-        if (h_wins) cudaFreeHost(h_wins);
-        for (int k = 0; k < 2; k++) { if (h_stage[k]) cudaFreeHost(h_stage[k]); if (stage_done[k]) cudaEventDestroy(stage_done[k]); }
-    }
-};
-
+LURK_MSM_EXTERN(CurveBn254G1)
+LURK_MSM_EXTERN(CurveGrumpkin)
+LURK_MSM_EXTERN(CurvePallas)
+LURK_MSM_EXTERN(CurveVesta)
 }  // namespace lurk
 
 using namespace lurk;
-
-struct lurk_msm_ctx {
-    int curve_id = 0;
-    int device = 0;
-    size_t n = 0;
-    void *d_bases = nullptr;
-    bool owns_bases = false;
-    void *d_table = nullptr;      // fixed-base table (nwin x n affine), optional
-    bool owns_table = false;
-    int fixed_c = 0;
-    std::mutex mu;
-    MsmScratch scratch;
-    // optional device timing of the dominant kernel (bucket accumulation), on the launching stream
-    bool profile = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float last_accumulate_ms = 0.f;
-    unsigned last_launches = 0;
-    // launch / finish split
-    bool pending = false;
-    int pending_fmt = 0, pending_c = 0, pending_nwin = 0;
-    bool pending_fixed = false;
-    uint32_t pending_vwin = 0, pending_nb = 0;
-    cudaEvent_t done = nullptr;
-};
-
-namespace lurk {
-
-template <class Fb>
-static void point_to_bytes(const XYZZ<Fb> &p, int fmt, uint8_t out[96]) {
-    memset(out, 0, 96);
-    if (p.is_identity()) return;
-    Affine<Fb> a = p.to_affine();
-    Fb one = Fb::one();
-    if (fmt == LURK_FMT_CANONICAL) { a.x = a.x.to_canonical(); a.y = a.y.to_canonical(); one = one.to_canonical(); }
-    memcpy(out, a.x.v, 32); memcpy(out + 32, a.y.v, 32); memcpy(out + 64, one.v, 32);
-}
-
-// enqueue the whole pipeline on stream s, ending with the async read-back of the window sums
-template <class C>
-static int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cudaStream_t s) {
-    using Fb = typename C::Base;
-    using Fs = typename C::Scalar;
-    using Pt = XYZZ<Fb>;
-    if (ctx->pending) { set_error("a launch is already pending on this context (call lurk_msm_ctx_finish)"); return LURK_ERR_ARG; }
-    if (!ctx->done) LURK_CUDA_TRY(cudaEventCreateWithFlags(&ctx->done, cudaEventDisableTiming));
-    ctx->pending_fmt = fmt;
-    ctx->pending_nwin = 0;
-    if (n == 0) { ctx->pending = true; return LURK_OK; }
-    const bool fixed = ctx->d_table != nullptr;
-    MsmPlan P = make_plan(n, Fs::Params::NBITS, fixed ? ctx->fixed_c : 0);
-    MsmScratch &S = ctx->scratch;
-    const uint32_t TB = P.total_buckets;
-    const uint32_t ntiles = (TB + SCAN_TILE - 1) / SCAN_TILE;
-    {
-        // scratch grows monotonically; a context is normally run at one size (the circuit's witness length)
-        auto ensure = [](DevBuf &b, size_t bytes) { return b.bytes >= bytes ? LURK_OK : b.alloc(bytes); };
-        LURK_TRY(ensure(S.counts, ((size_t)TB + 1) * 2 * sizeof(uint32_t)));   // counts | cursor
-        LURK_TRY(ensure(S.offsets, ((size_t)TB + 1) * sizeof(uint32_t)));
-        LURK_TRY(ensure(S.tiles, ((size_t)ntiles + 1) * 2 * sizeof(uint32_t)));  // tile sums | tile offsets
-        LURK_TRY(ensure(S.sorted, n * (size_t)P.nwin * sizeof(uint32_t)));
-        LURK_TRY(ensure(S.buckets, (size_t)TB * sizeof(Pt)));
-        LURK_TRY(ensure(S.pkey[0], (size_t)P.t1 * sizeof(uint32_t)));
-        LURK_TRY(ensure(S.ppt[0], (size_t)P.t1 * sizeof(Pt)));
-        size_t t2 = ((size_t)P.t1 + 7) / 8;
-        LURK_TRY(ensure(S.pkey[1], t2 * sizeof(uint32_t)));
-        LURK_TRY(ensure(S.ppt[1], t2 * sizeof(Pt)));
-        LURK_TRY(ensure(S.chunks, (size_t)(TB / P.chunk) * sizeof(Pt)));
-        if (fixed) LURK_TRY(ensure(S.chunk_sums, (size_t)(TB / P.chunk) * sizeof(Pt)));
-        LURK_TRY(ensure(S.wins, 128 * sizeof(Pt)));
-        if (!S.h_wins) LURK_CUDA_TRY(cudaMallocHost(&S.h_wins, 128 * sizeof(Pt)));
-    }
-    if (ntiles > 4096) { set_error("bucket table too large for the scan"); return LURK_ERR_ARG; }
-    uint32_t *counts = S.counts.as<uint32_t>();
-    uint32_t *cursor = counts + (TB + 1);
-    uint32_t *offsets = S.offsets.as<uint32_t>();
-    uint32_t *tile_sums = S.tiles.as<uint32_t>(), *tile_offsets = tile_sums + (ntiles + 1);
-    uint32_t *sorted = S.sorted.as<uint32_t>();
-    Pt *buckets = S.buckets.as<Pt>();
-
-    LURK_CUDA_TRY(cudaMemsetAsync(counts, 0, ((size_t)TB + 1) * 2 * sizeof(uint32_t), s));
-    LURK_CUDA_TRY(cudaMemsetAsync(buckets, 0, (size_t)TB * sizeof(Pt), s));   // all-zero = identity
-    const unsigned gs = (unsigned)((n + 255) / 256);
-    unsigned launches = 0;
-    const uint32_t key_stride = fixed ? 0u : P.nb;                 // fixed-base: all windows share one bucket set
-    const uint32_t base_stride = fixed ? (uint32_t)ctx->n : 0u;     // ... and address table[w * n + i]
-    const Affine<Fb> *bases = (const Affine<Fb> *)(fixed ? ctx->d_table : ctx->d_bases);
-    msm_count_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, key_stride, counts);
-    msm_scan_tile_sums_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_sums);
-    msm_scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_sums, ntiles, tile_offsets);
-    msm_scan_apply_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_offsets, ntiles, offsets);
-    msm_scatter_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, key_stride, base_stride, offsets, cursor, sorted);
-    if (ctx->profile) cudaEventRecord(ctx->ev0, s);
-    if (fixed)
-        msm_accumulate_kernel<Fb, 5><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
-                                                                       S.ppt[0].as<Pt>(), P.seg, P.t1);
-    else
-        msm_accumulate_kernel<Fb, 4><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
-                                                                       S.ppt[0].as<Pt>(), P.seg, P.t1);
-    if (ctx->profile) cudaEventRecord(ctx->ev1, s);
-    launches += 6;
-    // shrinking passes over the partial list: one throughput-shaped pass (8 entries per thread), then warp-cooperative
-    // passes (32x per pass, 5 dependent additions each) until a single warp finishes
-    uint32_t count = P.t1;
-    int cur = 0;
-    if (count > 32) {
-        const uint32_t seg2 = 8, threads = (count + seg2 - 1) / seg2;
-        msm_partial_kernel<Fb><<<(threads + 127) / 128, 128, 0, s>>>(S.pkey[cur].as<uint32_t>(), S.ppt[cur].as<Pt>(), count, buckets,
-                                                                    S.pkey[cur ^ 1].as<uint32_t>(), S.ppt[cur ^ 1].as<Pt>(), seg2, 0);
-        launches++;
-        count = threads;
-        cur ^= 1;
-    }
-    for (;;) {
-        const uint32_t warps = (count + 31) / 32;
-        const int last = warps == 1;
-        msm_partial_warp_kernel<Fb><<<(warps * 32 + 127) / 128, 128, 0, s>>>(S.pkey[cur].as<uint32_t>(), S.ppt[cur].as<Pt>(), count, buckets,
-                                                                            S.pkey[cur ^ 1].as<uint32_t>(), S.ppt[cur ^ 1].as<Pt>(), last);
-        launches++;
-        if (last) break;
-        count = warps;
-        cur ^= 1;
-    }
-    const uint32_t nchunks = TB / P.chunk;
-    msm_bucket_reduce_kernel<Fb><<<(nchunks + 127) / 128, 128, 0, s>>>(buckets, P.nb, P.chunk, nchunks, S.chunks.as<Pt>(),
-                                                                       fixed ? S.chunk_sums.as<Pt>() : nullptr);
-    msm_window_sum_kernel<Fb><<<P.vwin, 256, 0, s>>>(S.chunks.as<Pt>(), P.nb / P.chunk, S.wins.as<Pt>());
-    launches += 2;
-    if (fixed) { msm_window_sum_kernel<Fb><<<P.vwin, 256, 0, s>>>(S.chunk_sums.as<Pt>(), P.nb / P.chunk, S.wins.as<Pt>() + 64); launches++; }
-    ctx->last_launches = launches;
-    LURK_CUDA_TRY(cudaGetLastError());
-    LURK_CUDA_TRY(cudaMemcpyAsync(S.h_wins, S.wins.p, (size_t)(fixed ? 128 : P.vwin) * sizeof(Pt), cudaMemcpyDeviceToHost, s));
-    LURK_CUDA_TRY(cudaEventRecord(ctx->done, s));
-    ctx->pending = true;
-    ctx->pending_c = P.c;
-    ctx->pending_nwin = P.nwin;
-    ctx->pending_fixed = fixed;
-    ctx->pending_vwin = P.vwin;
-    ctx->pending_nb = P.nb;
-    return LURK_OK;
-}
-
-// wait for the read-back, Horner over the windows on the host, one inversion to affine
-template <class C>
-static int msm_finish(lurk_msm_ctx *ctx, uint8_t out[96]) {
-    using Fb = typename C::Base;
-    using Pt = XYZZ<Fb>;
-    if (!ctx->pending) { set_error("no launch pending on this context"); return LURK_ERR_ARG; }
-    ctx->pending = false;
-    if (ctx->pending_nwin == 0) { memset(out, 0, 96); return LURK_OK; }
-    LURK_CUDA_TRY(cudaEventSynchronize(ctx->done));
-    if (ctx->profile) cudaEventElapsedTime(&ctx->last_accumulate_ms, ctx->ev0, ctx->ev1);
-    const Pt *w = reinterpret_cast<const Pt *>(ctx->scratch.h_wins);
-    Pt acc = Pt::identity();
-    if (ctx->pending_fixed) {
-        // shared bucket set cut into virtual windows: sum_v R_v + nb * sum_v v S_v; the weighted sum is a running sum
-        // over the (<= 16) virtual windows, nb is a power of two
-        Pt run = Pt::identity(), wsum = Pt::identity();
-        for (uint32_t v = ctx->pending_vwin; v-- > 1;) { run.add(w[64 + v]); wsum.add(run); }
-        for (uint32_t b = ctx->pending_nb; b > 1; b >>= 1) wsum = wsum.dbl();
-        for (uint32_t v = 0; v < ctx->pending_vwin; v++) acc.add(w[v]);
-        acc.add(wsum);
-    } else {
-        for (int i = ctx->pending_nwin - 1; i >= 0; i--) {
-            for (int d = 0; d < ctx->pending_c; d++) acc = acc.dbl();
-            acc.add(w[i]);
-        }
-    }
-    point_to_bytes(acc, ctx->pending_fmt, out);
-    return LURK_OK;
-}
-
-template <class C>
-static int msm_run(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, uint8_t out[96], cudaStream_t s) {
-    LURK_TRY(msm_launch<C>(ctx, d_scalars, n, fmt, s));
-    return msm_finish<C>(ctx, out);
-}
-
-template <class C>
-static int ctx_upload(lurk_msm_ctx *ctx, const uint8_t *bases, size_t n, int fmt) {
-    using Fb = typename C::Base;
-    LURK_CUDA_TRY(cudaMalloc(&ctx->d_bases, n * 64));
-    ctx->owns_bases = true;
-    LURK_CUDA_TRY(cudaMemcpy(ctx->d_bases, bases, n * 64, cudaMemcpyHostToDevice));
-    int bad = 0;
-    LURK_TRY(check_reduced_dev<Fb>(ctx->d_bases, n * 2, 0, &bad));
-    if (bad) { set_error("%d base coordinate(s) are not reduced below the field modulus", bad); return LURK_ERR_RANGE; }
-    if (fmt == LURK_FMT_CANONICAL) {
-        msm_bases_to_mont_kernel<Fb><<<sm_count() * 8, 256>>>((Fb *)ctx->d_bases, n * 2);
-        LURK_CUDA_TRY(cudaGetLastError());
-        LURK_CUDA_TRY(cudaDeviceSynchronize());
-    }
-    return LURK_OK;
-}
-
-}  // namespace lurk
 
 extern "C" {
 
@@ -706,23 +89,7 @@ int lurk_msm_ctx_precompute(lurk_msm_ctx *ctx) {
     std::lock_guard<std::mutex> g(ctx->mu);
     if (ctx->d_table || ctx->n == 0) return LURK_OK;
     if (ctx->pending) { set_error("a launch is pending on this context"); return LURK_ERR_ARG; }
-    return dispatch_curve(ctx->curve_id, [&](auto cv) {
-        using Cv = decltype(cv);
-        using Fb = typename Cv::Base;
-        const int c = fixed_base_window(ctx->n);
-        const int nwin = Cv::Scalar::Params::NBITS / c + 1;
-        if (nwin > MSM_MAX_TABLE_WINDOWS || (uint64_t)nwin * ctx->n >= (1ull << 31)) { set_error("commitment key too large for a fixed-base table"); return LURK_ERR_ARG; }
-        void *t = nullptr;
-        LURK_CUDA_TRY(cudaMalloc(&t, (size_t)nwin * ctx->n * sizeof(Affine<Fb>)));
-        msm_precompute_kernel<Fb><<<(unsigned)((ctx->n + 127) / 128), 128>>>((const Affine<Fb> *)ctx->d_bases, ctx->n, c, nwin, (Affine<Fb> *)t);
-        cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { cudaFree(t); set_error("fixed-base precomputation failed: %s", cudaGetErrorString(e)); return LURK_ERR_CUDA; }
-        ctx->d_table = t;
-        ctx->owns_table = true;
-        ctx->fixed_c = c;
-        return LURK_OK;
-    });
+    return dispatch_curve(ctx->curve_id, [&](auto cv) { return msm_precompute<decltype(cv)>(ctx); });
 }
 
 int lurk_msm_ctx_clone(lurk_msm_ctx *ctx, lurk_msm_ctx **out) {

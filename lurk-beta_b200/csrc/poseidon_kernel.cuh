@@ -395,7 +395,7 @@ struct PoseidonInstance {
 };
 
 template <class F>
-static PoseidonInstance<F> &instance(int arity) {
+PoseidonInstance<F> &instance(int arity) {
     static std::mutex mu;
     static std::map<int, std::unique_ptr<PoseidonInstance<F>>> cache;   // mirrors OnceCell in src/hash.rs:42-46
     std::lock_guard<std::mutex> g(mu);
@@ -415,7 +415,7 @@ static PoseidonInstance<F> &instance(int arity) {
 }
 
 template <class F>
-static int device_consts(PoseidonInstance<F> &inst, const F **out) {
+int device_consts(PoseidonInstance<F> &inst, const F **out) {
     static std::mutex mu;
     std::lock_guard<std::mutex> g(mu);
     int dev = 0;
@@ -433,7 +433,7 @@ static int device_consts(PoseidonInstance<F> &inst, const F **out) {
 }
 
 template <class F, int ARITY, bool WITNESS>
-static int launch_one(const F *d_consts, const PoseidonInstance<F> &inst, const void *d_pre, size_t n, void *d_out,
+int launch_one(const F *d_consts, const PoseidonInstance<F> &inst, const void *d_pre, size_t n, void *d_out,
                       const uint64_t *d_offs, int in_fmt, int out_fmt, int grid, int block, cudaStream_t s) {
     constexpr int T = ARITY + 1;
     constexpr int BIG = ARITY >= 6 ? 384 : 512;
@@ -454,7 +454,7 @@ static int launch_one(const F *d_consts, const PoseidonInstance<F> &inst, const 
 }
 
 template <class F, int ARITY, bool WITNESS>
-static int launch_arity(const void *d_pre, size_t n, void *d_out, const uint64_t *d_offs, int in_fmt, int out_fmt, cudaStream_t s) {
+int launch_arity(const void *d_pre, size_t n, void *d_out, const uint64_t *d_offs, int in_fmt, int out_fmt, cudaStream_t s) {
     if (n == 0) return LURK_OK;
     PoseidonInstance<F> &inst = instance<F>(ARITY);
     const F *d_consts = nullptr;
@@ -513,11 +513,5 @@ int launch_bitdecomp(const void *d_values, size_t n, void *d_blocks, int blk, in
     LURK_CUDA_TRY(cudaGetLastError());
     return LURK_OK;
 }
-
-#define LURK_POSEIDON_INSTANTIATE(F)                                                                                  \
-    template int launch_poseidon<F, false>(int, const void *, size_t, void *, int, int, cudaStream_t, const uint64_t *); \
-    template int launch_poseidon<F, true>(int, const void *, size_t, void *, int, int, cudaStream_t, const uint64_t *);  \
-    template int poseidon_instance_info<F>(int, const PoseidonParams<F> **, PoseidonLayout *);                        \
-    template int launch_bitdecomp<F>(const void *, size_t, void *, int, int, cudaStream_t, const uint64_t *);
 
 }  // namespace lurk
