@@ -141,3 +141,20 @@ def test_msm_fixed_base_table_same_results(L, oracle, spec, curve):
     clone = ck.clone()
     sc = scalars_for(spec, curve, 1000, seed=9, shape="uniform")
     assert np.array_equal(clone.commit(sc), oracle.msm(curve, bases[:64000], sc))
+
+
+@pytest.mark.parametrize("n", [3, 31, 32, 33, 63, 65, 127, 1023, 1025, 4097, 20011, 65537])
+def test_msm_sizes_around_plan_boundaries(L, oracle, spec, n):
+    """window width, segment length and the number of partial passes all change with n: sweep sizes around the
+    boundaries, plain and fixed-base, scalars with long zero runs in the high windows"""
+    curve = [0, 2, 1, 3][n % 4]
+    bases = oracle.gen_bases(curve, n)
+    sf = spec.CURVES[curve]["scalar"]
+    sc = scalars_for(spec, curve, n, seed=n, shape="witness" if n % 2 else "uniform")
+    want = oracle.msm(curve, bases, sc, nthreads=8, naive=(n < 40))
+    ck = L.CommitmentKey(curve, bases)
+    assert np.array_equal(ck.commit(sc), want)
+    ck.precompute()
+    assert np.array_equal(ck.commit(sc), want)
+    m = max(1, n // 3)                                   # a shorter scalar vector on the same (fixed-base) key
+    assert np.array_equal(ck.commit(sc[:32 * m]), oracle.msm(curve, bases[:64 * m], sc[:32 * m], nthreads=8, naive=(m < 40)))

@@ -106,3 +106,35 @@ def test_limb_arithmetic_against_bigints(fieldlib, spec, field):
         B = [p - 1] * k if trial < 30 else [rnd.randrange(p) for _ in range(k)]
         fieldlib.fe_test_dot(field, k, b"".join(x.to_bytes(32, "little") for x in A), b"".join(x.to_bytes(32, "little") for x in B), out)
         assert int.from_bytes(out.raw, "little") == sum(x * y for x, y in zip(A, B)) % p
+
+
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+def test_host_group_law_properties(L, spec, curve):
+    """host-side XYZZ arithmetic of the library (used for the N-GPU combine and the final MSM window combine) against the
+    affine chord-and-tangent law of the Python spec: random multiples of G, doubling, inverse pairs, identity handling"""
+    from hypothesis import given, settings, strategies as st
+    C = spec.CURVES[curve]
+    pb = spec.FIELD_MODULUS[C["base"]]
+    G = C["gen"]
+    mults = {k: spec.ec_mul(k, G, pb) for k in range(1, 40)}
+
+    def rec(pt):
+        return pack([0, 0, 0]) if pt is None else pack([pt[0], pt[1], 1])
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(min_value=-39, max_value=39), min_size=0, max_size=12))
+    def check(ks):
+        pts, want = [], None
+        for k in ks:
+            if k == 0:
+                pts.append(None)
+                continue
+            p = mults[abs(k)]
+            if k < 0:
+                p = (p[0], (pb - p[1]) % pb)
+            pts.append(p)
+            want = spec.ec_add(want, p, pb)
+        buf = np.concatenate([rec(p) for p in pts]) if pts else np.zeros(0, dtype=np.uint8)
+        got = L.point_sum(curve, buf)
+        assert np.array_equal(got, rec(want))
+    check()
