@@ -7,6 +7,9 @@
 //   * the first min(log_n, 10) butterfly stages run inside shared memory on 1024-element tiles after a
 //     bit-reversal gather (one global read + one global write for 10 stages);
 //   * the remaining stages are strided global passes, two stages (radix-4) per pass where possible.
+// For 256-bit fields the butterflies' multiplier work (12 x 2^24 products = 2.9 ms on the IMAD pipe at 2^24) exceeds the HBM
+// time of the passes, so the transform is multiply bound like the rest of the path (4.1 ms measured).  A variant that ran
+// stages 11..20 on shared-memory column tiles (4 global passes instead of 9) was measured slower (4.7 ms) and dropped.
 // Natural order in, natural order out, Montgomery form, in place.
 #include "common.cuh"
 

@@ -130,7 +130,7 @@ def test_fold_helpers_parity(L, oracle, spec, field):
 
 
 @pytest.mark.parametrize("field", [0, 2, 3])
-@pytest.mark.parametrize("log_n", [1, 4, 10, 13, 16])
+@pytest.mark.parametrize("log_n", [1, 4, 10, 11, 13, 16, 20, 21, 22])
 def test_ntt_parity(L, oracle, spec, field, log_n):
     import torch
     lib = L._capi.lib()
