@@ -9,7 +9,6 @@ import torch
 sys.path.insert(0, ".")
 sys.path.insert(0, "tests")
 import lurk_beta_b200 as L
-from oracle import capi as oracle
 from util import random_elements
 
 lib = L._capi.lib()
@@ -42,10 +41,9 @@ def poseidon(field, arity, logn):
 
 def msm(curve, logn, shape, fixed=False):
     n = 1 << logn
-    from oracle import spec
     t0 = time.time()
-    bases = oracle.gen_bases(curve, n)
-    sc = random_elements(spec.CURVES[curve]["scalar"], n, seed=2, shape=shape)
+    bases = L.synthetic_bases(curve, n)
+    sc = random_elements([0, 1, 2, 3][curve], n, seed=2, shape=shape)
     ck = L.CommitmentKey(curve, bases)
     if fixed:
         ck.precompute()
