@@ -51,9 +51,11 @@ class NovaFoldPipeline:
         self.mv1 = [torch.empty(n_t * 32, dtype=torch.uint8, device="cuda") for _ in range(3)]
         nb = len(z2_buffers)                                    # stage A may run nb - 1 steps ahead of stage B
         self.mv2 = [[torch.empty(n_t * 32, dtype=torch.uint8, device="cuda") for _ in range(3)] for _ in range(nb)]
-        self.sK = [torch.cuda.Stream() for _ in range(3)]      # slot-witness kernels (one stream per slot type), commit(W)
-        self.sA = torch.cuda.Stream()                          # Az2, Bz2, Cz2 of the prefetched step
-        self.sB = torch.cuda.Stream()                          # Az1.., cross term, commit(T), fold
+        # The fold chain (stage B) is the critical path: its stream gets the high CUDA priority so that the short,
+        # latency-bound tail kernels of commit(T) are not queued behind the thousands of CTAs of a prefetched commit(W).
+        self.sK = [torch.cuda.Stream(priority=0) for _ in range(3)]   # slot-witness kernels (one stream per slot type), commit(W)
+        self.sA = torch.cuda.Stream(priority=0)                       # Az2, Bz2, Cz2 of the prefetched step
+        self.sB = torch.cuda.Stream(priority=-1)                      # Az1.., cross term, commit(T), fold
         self.ckW = [ck] + [ck.clone() for _ in range(nb - 1)]
         self.ckT = ck.clone()
         for c in (*self.ckW, self.ckT):
