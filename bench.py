@@ -215,7 +215,7 @@ class FoldStepGPU:
             sb = [SlotBatch(a, n, 0, self.slot_pre_dev[a][b], d_offsets=offs) for a, n, offs, _blk in self.slot_layout]
             sb.append(SlotBatch(0, self.bd_n, 0, self.bd_dev[b], d_offsets=self.bd_offs))
             self.slot_batches.append(sb)
-        self.sS = t.cuda.Stream()                          # secondary-circuit commitments
+        self.sS = t.cuda.Stream(priority=-1)               # secondary-circuit commitments (tiny: let them through at once)
         self.ck2b = self.ck2.clone()
         self.prefetched = -1                               # last step index whose stage A has been enqueued
         self.step_index = 0

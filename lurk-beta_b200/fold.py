@@ -118,9 +118,10 @@ class NovaFoldPipeline:
         self.launches_A = k
 
     # ---------------------------------------------------------------------------------------------- stage B
-    def stage_b(self, b, challenge):
-        """fold step on buffer b; returns (comm_W, comm_T) as 96-byte points (Montgomery)"""
-        t, lib, chk = self.t, self.lib, _capi.check
+    def stage_b_launch(self, b):
+        """enqueue the chain-dependent kernels of the step on buffer b: Az1.., cross term, commit(T).  Call it right after
+        the previous step's fold has been enqueued (stage_b_collect) so the GPU never waits for the host."""
+        lib, chk = self.lib, _capi.check
         M = _capi.FMT_MONTGOMERY
         sb = C.c_void_p(self.sB.cuda_stream)
         k = 0
@@ -135,6 +136,15 @@ class NovaFoldPipeline:
                                     cz2.data_ptr(), _capi.np_ptr(self.u1), _capi.np_ptr(self.u2), self.n_t, self.T.data_ptr(), sb))
         k += 1
         self.ckT.launch_device(self.T.data_ptr(), self.n_t, fmt=M, stream=self.sB.cuda_stream)
+        self._k_launch = k
+
+    def stage_b_collect(self, b, challenge):
+        """wait for commit(W2[b]) and commit(T), exchange partial commitments if the key is sharded, derive the challenge
+        and enqueue the fold; returns (comm_W, comm_T) as 96-byte points (Montgomery)"""
+        t, lib, chk = self.t, self.lib, _capi.check
+        M = _capi.FMT_MONTGOMERY
+        sb = C.c_void_p(self.sB.cuda_stream)
+        k = self._k_launch
         cw = self.ckW[b].finish()
         ms, kl = self.ckW[b].last_profile()
         self.accumulate_ms.append(ms)
@@ -160,6 +170,11 @@ class NovaFoldPipeline:
         self.ev_fold[b].record(self.sB)
         self.launches_B = k
         return cw, ct
+
+    def stage_b(self, b, challenge):
+        """launch + collect in one call (no software pipelining of the host side)"""
+        self.stage_b_launch(b)
+        return self.stage_b_collect(b, challenge)
 
     def drain(self, b):
         """collect a prefetched commit(W) that will not be folded"""
