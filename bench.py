@@ -489,7 +489,9 @@ def run_reference(args):
         "unit": "iterations/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64x4 (254-bit Montgomery integers)", "data": "synthetic",
-        "config": {"workload": "fib rc=100 Nova IVC fold step on BN254/Grumpkin (benches/fibonacci.rs), composed CPU kernels",
+        "config": {"workload": "fib rc=100 Nova IVC fold step on BN254/Grumpkin (benches/fibonacci.rs, configs[0]/metric config)",
+                   "composed": "the same per-fold work as the B200 arm (2100 Poseidon slot witnesses + 300 bit-decomps, commit(W), 6 SpMV + cross term, "
+                               "commit(T), 2 AXPY, 2 secondary commits) on the host cores through oracle/oracle.c",
                    "rc_sample": rc},
         "cpu_baseline": {"value": round(value, 3), "unit": "iterations/s", "cores": wl.threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
