@@ -69,17 +69,19 @@ class PoseidonCache:
         if arity not in HASH_ARITIES:
             raise ValueError(f"unsupported arity: {arity}")   # reference: panic!("unsupported arity"), src/hash.rs:26
         memo = self._memo[arity]
-        todo = []
+        keys, todo, seen = [], [], set()
         for p in preimages:
             key = tuple(int(x) for x in p)
             if len(key) != arity:
                 raise ValueError(f"preimage of length {len(key)} for arity {arity}")
-            if key not in memo and key not in todo:
+            keys.append(key)
+            if key not in memo and key not in seen:
+                seen.add(key)
                 todo.append(key)
         if todo:
             digests = unpack(self.hash_batch_bytes(arity, pack([x for k in todo for x in k])))
             memo.update(zip(todo, digests))
-        return [memo[tuple(int(x) for x in p)] for p in preimages]
+        return [memo[k] for k in keys]
 
     # -- the reference's single-hash surface
     def compute_hash(self, preimage):
