@@ -23,11 +23,9 @@ of the two 96-byte partial commitments per step followed by local point addition
 prover is Rust and cannot run in this image.
 """
 import argparse
-import ctypes as C
 import hashlib
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

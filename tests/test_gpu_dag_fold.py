@@ -1,6 +1,4 @@
 """GPU parity for S2 (store hydration), S5 (fold helpers) and K6 (NTT) against the oracle."""
-import ctypes as C
-
 import numpy as np
 import pytest
 

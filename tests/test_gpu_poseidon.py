@@ -51,7 +51,6 @@ def test_digest_parity_throughput_path(L, oracle, field, arity):
 
 
 def test_digest_montgomery_entry_point(L, oracle, spec):
-    import ctypes as C
     field, arity, n = 0, 4, 100
     p = spec.FIELD_MODULUS[field]
     pre = random_elements(field, n * arity, seed=4)

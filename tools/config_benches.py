@@ -4,7 +4,6 @@ line).  bench.py stays the contract for the headline metric; this produces the p
   single process:  python tools/config_benches.py
   N GPUs:          python -m torch.distributed.run --nproc-per-node N ... tools/config_benches.py --only msm24"""
 import argparse
-import ctypes as C
 import json
 import os
 import sys

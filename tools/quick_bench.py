@@ -1,5 +1,4 @@
 """Ad-hoc device timings of the individual kernels (development aid; bench.py is the contract)."""
-import ctypes as C
 import sys
 import time
 
