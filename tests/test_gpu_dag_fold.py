@@ -170,3 +170,25 @@ def test_trie_coprocessor_mirror_goldens(L, oracle):
     assert w.size == 85 * 396 * 32                                        # 85 x hash8 slot blocks (a12: ~1.08 MB of aux)
     pre = pack([x for p in t.prove_lookup_at_path(t.path(123)) for x in p])
     assert np.array_equal(w, oracle.poseidon_witness_batch(0, 8, pre, nthreads=4))
+
+
+def test_store_lambda_commitment_golden(L):
+    """G9 through the store mirror on the GPU: a Fun is a tuple4 -> H8 (src/lem/store.rs:51-67,623-626)"""
+    NIL, CONS, FUN, ENV = 0, 1, 3, 12
+    s = L.StoreCore(L.FIELD_BN254_FR)
+    zero_str, zero_sym = s.intern_atom(TAG_STR, 0), s.intern_atom(TAG_SYM, 0)
+
+    def intern_sym(path):
+        sym = zero_sym
+        for name in path:
+            st = zero_str
+            for ch in reversed(name):
+                st = s.intern_tuple2([s.intern_atom(TAG_CHAR, ord(ch)), st], TAG_STR)
+            sym = s.intern_tuple2([st, sym], TAG_SYM)
+        return sym
+
+    x = intern_sym(["lurk", "user", "x"])
+    nil = (NIL, intern_sym(["lurk", "nil"])[1])
+    vars_ = s.intern_tuple2([x, nil], CONS)
+    fun = s.intern_tuple4([vars_, x, s.intern_atom(ENV, 0), s.intern_atom(NIL, 0)], FUN)
+    assert s.hide(0, fun) == GOLDEN["G9"]

@@ -188,3 +188,14 @@ def test_trie_insert_golden(oracle):
         pre[path(key, height)[depth]] = v
         v = h(oracle, BN, pre)
     assert v == GOLDEN["G10"]
+
+
+def test_lambda_commitment_golden_tuple4(oracle):
+    """G9: (commit (lambda (x) x)).  Fun = tuple4 [vars, body, env, dummy] (src/lem/eval.rs:1158-1186: cons4(vars, body, env,
+    foo); src/lem/store.rs:623-626) -> arity 8 with mixed tags; vars = ((x)), body = x, x = .lurk.user.x, empty env = (Env, 0)."""
+    NIL, CONS, SYM, FUN, ENV = 0, 1, 2, 3, 12
+    x = lurk_sym(oracle, ["lurk", "user", "x"])
+    nil = lurk_sym(oracle, ["lurk", "nil"])
+    vars_ = h(oracle, BN, [SYM, x, NIL, nil])
+    fun = h(oracle, BN, [CONS, vars_, SYM, x, ENV, 0, NIL, 0])
+    assert h(oracle, BN, [0, FUN, fun]) == GOLDEN["G9"]
