@@ -192,3 +192,38 @@ def test_store_lambda_commitment_golden(L):
     vars_ = s.intern_tuple2([x, nil], CONS)
     fun = s.intern_tuple4([vars_, x, s.intern_atom(ENV, 0), s.intern_atom(NIL, 0)], FUN)
     assert s.hide(0, fun) == GOLDEN["G9"]
+
+
+def test_store_proof_claim_golden(L):
+    """G11 (tests/lurk-cli-tests.rs:58) through the store mirror on the GPU: the claim of `!(prove (+ 1 1))` is a DAG of
+    H4 nodes (strings, symbol paths, keywords, conses) hydrated in one lurk_dag_hash call, then hidden with secret 0."""
+    NIL, CONS, NUM, KEY, ENV = 0, 1, 4, 10, 12
+    s = L.StoreCore(L.FIELD_BN254_FR)
+    zero_str, zero_sym = s.intern_atom(TAG_STR, 0), s.intern_atom(TAG_SYM, 0)
+
+    def intern_sym(path, tag=TAG_SYM):
+        sym = zero_sym
+        for name in path:
+            st = zero_str
+            for ch in reversed(name):
+                st = s.intern_tuple2([s.intern_atom(TAG_CHAR, ord(ch)), st], TAG_STR)
+            sym = s.intern_tuple2([st, sym], TAG_SYM)
+        return (tag, sym[1])
+
+    nil = intern_sym(["lurk", "nil"], NIL)
+    num = lambda v: s.intern_atom(NUM, v)
+    cons = lambda a, b: s.intern_tuple2([a, b], CONS)
+
+    def lst(items):
+        acc = nil
+        for it in reversed(items):
+            acc = cons(it, acc)
+        return acc
+
+    key = lambda name: intern_sym([name], KEY)
+    env = s.intern_atom(ENV, 0)
+    expr = lst([intern_sym(["lurk", "+"]), num(1), num(1)])
+    cont, cont_out = cons(num(0x1000), num(GOLDEN["G1"])), cons(num(0x100E), num(GOLDEN["G1"]))
+    claim = lst([key("expr"), expr, key("env"), env, key("cont"), cont,
+                 key("expr-out"), num(2), key("env-out"), env, key("cont-out"), cont_out])
+    assert s.hide(0, claim) == GOLDEN["G11"]

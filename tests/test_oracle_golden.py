@@ -1,5 +1,5 @@
 """Pins the oracle (oracle/spec.py and oracle/oracle.c) on every golden vector the reference's own tests hold for
-the Poseidon path (SURVEY.md 8(c) G1..G8, G12) and on the sizes it pins (witness sizes, bit-decomposition sizes)."""
+the Poseidon path (SURVEY.md 8(c) G1..G12) and on the sizes it pins (witness sizes, bit-decomposition sizes)."""
 import hashlib
 
 import numpy as np
@@ -199,3 +199,31 @@ def test_lambda_commitment_golden_tuple4(oracle):
     vars_ = h(oracle, BN, [SYM, x, NIL, nil])
     fun = h(oracle, BN, [CONS, vars_, SYM, x, ENV, 0, NIL, 0])
     assert h(oracle, BN, [0, FUN, fun]) == GOLDEN["G9"]
+
+
+def test_proof_claim_golden(oracle):
+    """G11: the claim hash inside the proof key the CLI test expects for `!(prove (+ 1 1))` (tests/lurk-cli-tests.rs:58).
+    claim = list(:expr e :env env :cont (tag . hash) :expr-out e' :env-out env' :cont-out (tag' . hash')) with continuations
+    given as conses of two Nums (src/cli/repl/mod.rs:263-296); claim hash = non-hiding commitment to it (:332).  Keywords
+    are Key-tagged symbol paths without a package prefix (src/lem/store.rs:489-505,603-605); Outermost/Terminal are
+    continuation atoms whose hash is H8(0^8) (src/lem/eval.rs:1415-1418); the final environment is the empty one."""
+    NIL, CONS, NUM, KEY, ENV = 0, 1, 4, 10, 12
+    OUTERMOST, TERMINAL = 0x1000, 0x100E                           # src/tag.rs:126-146
+    nil = (NIL, lurk_sym(oracle, ["lurk", "nil"]))
+    cons = lambda a, b: (CONS, h(oracle, BN, [a[0], a[1], b[0], b[1]]))
+
+    def lst(items):
+        acc = nil
+        for it in reversed(items):
+            acc = cons(it, acc)
+        return acc
+
+    key = lambda name: (KEY, lurk_sym(oracle, [name]))
+    num = lambda v: (NUM, v)
+    expr = lst([(TAG_SYM, lurk_sym(oracle, ["lurk", "+"])), num(1), num(1)])
+    env = (ENV, 0)
+    cont = cons(num(OUTERMOST), num(GOLDEN["G1"]))
+    cont_out = cons(num(TERMINAL), num(GOLDEN["G1"]))
+    claim = lst([key("expr"), expr, key("env"), env, key("cont"), cont,
+                 key("expr-out"), num(2), key("env-out"), env, key("cont-out"), cont_out])
+    assert h(oracle, BN, [0, claim[0], claim[1]]) == GOLDEN["G11"]
