@@ -194,36 +194,64 @@ def test_store_lambda_commitment_golden(L):
     assert s.hide(0, fun) == GOLDEN["G9"]
 
 
-def test_store_proof_claim_golden(L):
-    """G11 (tests/lurk-cli-tests.rs:58) through the store mirror on the GPU: the claim of `!(prove (+ 1 1))` is a DAG of
-    H4 nodes (strings, symbol paths, keywords, conses) hydrated in one lurk_dag_hash call, then hidden with secret 0."""
-    NIL, CONS, NUM, KEY, ENV = 0, 1, 4, 10, 12
-    s = L.StoreCore(L.FIELD_BN254_FR)
-    zero_str, zero_sym = s.intern_atom(TAG_STR, 0), s.intern_atom(TAG_SYM, 0)
+class _StoreExprs:
+    """expression builder over the store mirror (same shapes as tests/test_oracle_golden.py::_Exprs, but as store pointers
+    hydrated on the GPU)"""
+    NIL, CONS, FUN, NUM, KEY, ENV = 0, 1, 3, 4, 10, 12
 
-    def intern_sym(path, tag=TAG_SYM):
-        sym = zero_sym
+    def __init__(self, L):
+        self.s = s = L.StoreCore(L.FIELD_BN254_FR)
+        self.zero_str, self.zero_sym = s.intern_atom(TAG_STR, 0), s.intern_atom(TAG_SYM, 0)
+        self.nil = self.sym("lurk", "nil", tag=self.NIL)
+        self.env0 = s.intern_atom(self.ENV, 0)
+
+    def sym(self, *path, tag=TAG_SYM):
+        s, sym = self.s, self.zero_sym
         for name in path:
-            st = zero_str
+            st = self.zero_str
             for ch in reversed(name):
                 st = s.intern_tuple2([s.intern_atom(TAG_CHAR, ord(ch)), st], TAG_STR)
             sym = s.intern_tuple2([st, sym], TAG_SYM)
         return (tag, sym[1])
 
-    nil = intern_sym(["lurk", "nil"], NIL)
-    num = lambda v: s.intern_atom(NUM, v)
-    cons = lambda a, b: s.intern_tuple2([a, b], CONS)
+    def key(self, name): return self.sym(name, tag=self.KEY)
+    def num(self, v): return self.s.intern_atom(self.NUM, v)
+    def cons(self, a, b): return self.s.intern_tuple2([a, b], self.CONS)
 
-    def lst(items):
-        acc = nil
+    def lst(self, items):
+        acc = self.nil
         for it in reversed(items):
-            acc = cons(it, acc)
+            acc = self.cons(it, acc)
         return acc
 
-    key = lambda name: intern_sym([name], KEY)
-    env = s.intern_atom(ENV, 0)
-    expr = lst([intern_sym(["lurk", "+"]), num(1), num(1)])
-    cont, cont_out = cons(num(0x1000), num(GOLDEN["G1"])), cons(num(0x100E), num(GOLDEN["G1"]))
-    claim = lst([key("expr"), expr, key("env"), env, key("cont"), cont,
-                 key("expr-out"), num(2), key("env-out"), env, key("cont-out"), cont_out])
-    assert s.hide(0, claim) == GOLDEN["G11"]
+    def claim(self, expr, env, expr_out, env_out):
+        cont = self.cons(self.num(0x1000), self.num(GOLDEN["G1"]))
+        cont_out = self.cons(self.num(0x100E), self.num(GOLDEN["G1"]))
+        return self.lst([self.key("expr"), expr, self.key("env"), env, self.key("cont"), cont,
+                         self.key("expr-out"), expr_out, self.key("env-out"), env_out, self.key("cont-out"), cont_out])
+
+
+def test_store_proof_claim_golden(L):
+    """G11 (tests/lurk-cli-tests.rs:58) through the store mirror on the GPU: the claim of `!(prove (+ 1 1))` is a DAG of
+    H4 nodes (strings, symbol paths, keywords, conses) hydrated in one lurk_dag_hash call, then hidden with secret 0."""
+    e = _StoreExprs(L)
+    expr = e.lst([e.sym("lurk", "+"), e.num(1), e.num(1)])
+    assert e.s.hide(0, e.claim(expr, e.env0, e.num(2), e.env0)) == GOLDEN["G11"]
+
+
+def test_store_functional_commitment_goldens(L):
+    """G13/G14 (hiding commitment with a non-zero secret) and G16/G17 (demo/functional-commitment.lurk): one DAG mixing
+    tuple2 (H4), tuple4 (H8, the Fun) and a compact Env node (H4 with two tags dropped), hydrated on the GPU."""
+    e = _StoreExprs(L)
+    s = e.s
+    pair = e.cons(e.num(13), e.num(21))
+    assert s.hide(0, pair) == GOLDEN["G13"]
+    assert s.hide(12345, pair) == GOLDEN["G14"]
+    x, plus, mul = e.sym("lurk", "user", "x"), e.sym("lurk", "+"), e.sym("lurk", "*")
+    body = e.lst([plus, e.lst([mul, e.num(3), e.lst([mul, x, x])]), e.lst([plus, e.lst([mul, e.num(9), x]), e.num(2)])])
+    fun = s.intern_tuple4([e.lst([x]), body, e.env0, s.intern_atom(e.NIL, 0)], e.FUN)
+    comm = s.hide(0, fun)
+    assert comm == GOLDEN["G16"]
+    env = s.intern_compact([e.sym("lurk", "user", "f"), fun, e.env0], e.ENV)
+    expr = e.lst([e.lst([e.sym("lurk", "open"), e.num(comm)]), e.num(5)])
+    assert s.hide(0, e.claim(expr, env, e.num(122), e.env0)) == GOLDEN["G17"]

@@ -201,29 +201,71 @@ def test_lambda_commitment_golden_tuple4(oracle):
     assert h(oracle, BN, [0, FUN, fun]) == GOLDEN["G9"]
 
 
-def test_proof_claim_golden(oracle):
-    """G11: the claim hash inside the proof key the CLI test expects for `!(prove (+ 1 1))` (tests/lurk-cli-tests.rs:58).
-    claim = list(:expr e :env env :cont (tag . hash) :expr-out e' :env-out env' :cont-out (tag' . hash')) with continuations
-    given as conses of two Nums (src/cli/repl/mod.rs:263-296); claim hash = non-hiding commitment to it (:332).  Keywords
-    are Key-tagged symbol paths without a package prefix (src/lem/store.rs:489-505,603-605); Outermost/Terminal are
-    continuation atoms whose hash is H8(0^8) (src/lem/eval.rs:1415-1418); the final environment is the empty one."""
-    NIL, CONS, NUM, KEY, ENV = 0, 1, 4, 10, 12
+class _Exprs:
+    """Minimal expression builder over the oracle: z-pointers (tag, digest) of the shapes the reference's reader and REPL
+    produce (src/lem/store.rs:481-505 symbols, :603-605 keywords, list = right fold of Cons over nil)."""
+    NIL, CONS, FUN, NUM, KEY, ENV = 0, 1, 3, 4, 10, 12
     OUTERMOST, TERMINAL = 0x1000, 0x100E                           # src/tag.rs:126-146
-    nil = (NIL, lurk_sym(oracle, ["lurk", "nil"]))
-    cons = lambda a, b: (CONS, h(oracle, BN, [a[0], a[1], b[0], b[1]]))
 
-    def lst(items):
-        acc = nil
+    def __init__(self, oracle):
+        self.o = oracle
+        self.nil = (self.NIL, lurk_sym(oracle, ["lurk", "nil"]))
+        self.env0 = (self.ENV, 0)
+
+    def cons(self, a, b): return (self.CONS, h(self.o, BN, [a[0], a[1], b[0], b[1]]))
+    def num(self, v): return (self.NUM, v)
+    def sym(self, *path): return (TAG_SYM, lurk_sym(self.o, list(path)))
+    def key(self, name): return (self.KEY, lurk_sym(self.o, [name]))
+
+    def lst(self, items):
+        acc = self.nil
         for it in reversed(items):
-            acc = cons(it, acc)
+            acc = self.cons(it, acc)
         return acc
 
-    key = lambda name: (KEY, lurk_sym(oracle, [name]))
-    num = lambda v: (NUM, v)
-    expr = lst([(TAG_SYM, lurk_sym(oracle, ["lurk", "+"])), num(1), num(1)])
-    env = (ENV, 0)
-    cont = cons(num(OUTERMOST), num(GOLDEN["G1"]))
-    cont_out = cons(num(TERMINAL), num(GOLDEN["G1"]))
-    claim = lst([key("expr"), expr, key("env"), env, key("cont"), cont,
-                 key("expr-out"), num(2), key("env-out"), env, key("cont-out"), cont_out])
-    assert h(oracle, BN, [0, claim[0], claim[1]]) == GOLDEN["G11"]
+    def commit(self, secret, ptr): return h(self.o, BN, [secret, ptr[0], ptr[1]])
+
+    def claim_hash(self, expr, env, expr_out, env_out):
+        """src/cli/repl/mod.rs:263-296,332: list of keyword/value pairs, continuations as (Num tag . Num hash); Outermost and
+        Terminal are continuation atoms whose hash is H8(0^8) (src/lem/eval.rs:1415-1418)"""
+        cont = self.cons(self.num(self.OUTERMOST), self.num(GOLDEN["G1"]))
+        cont_out = self.cons(self.num(self.TERMINAL), self.num(GOLDEN["G1"]))
+        claim = self.lst([self.key("expr"), expr, self.key("env"), env, self.key("cont"), cont,
+                          self.key("expr-out"), expr_out, self.key("env-out"), env_out, self.key("cont-out"), cont_out])
+        return self.commit(0, claim)
+
+
+def test_proof_claim_golden(oracle):
+    """G11: the claim hash inside the proof key the CLI test expects for `!(prove (+ 1 1))` (tests/lurk-cli-tests.rs:58);
+    the final environment is the empty one (erased, src/lem/eval.rs:1417)."""
+    e = _Exprs(oracle)
+    expr = e.lst([e.sym("lurk", "+"), e.num(1), e.num(1)])
+    assert e.claim_hash(expr, e.env0, e.num(2), e.env0) == GOLDEN["G11"]
+
+
+def test_documented_commitment_examples(oracle):
+    """G13/G14: `!(commit '(13 . 21))` and `!(hide 12345 '(13 . 21))` (src/cli/repl/meta_cmd.rs:246-247,262-264): the second
+    is the only reference vector with a non-zero secret.  G15: proof key of `!(prove '(1 2 3))` (:359-361)."""
+    e = _Exprs(oracle)
+    pair = e.cons(e.num(13), e.num(21))
+    assert e.commit(0, pair) == GOLDEN["G13"]
+    assert e.commit(12345, pair) == GOLDEN["G14"]
+    l123 = e.lst([e.num(1), e.num(2), e.num(3)])
+    assert e.claim_hash(e.lst([e.sym("lurk", "quote"), l123]), e.env0, l123, e.env0) == GOLDEN["G15"]
+
+
+def test_functional_commitment_demo(oracle):
+    """G16/G17 (demo/functional-commitment.lurk): commitment to f = (lambda (x) (+ (* 3 (* x x)) (+ (* 9 x) 2))) defined at the
+    top level (closed over the empty env), and the claim of the proof of `!(call <G16> 5)`: expr = ((open <G16>) 5)
+    (src/cli/repl/meta_cmd.rs:530-548) evaluated in the REPL env {f -> Fun}; an Env is a *compact* node
+    H4[sym digest, val tag, val digest, env digest] (src/lem/store.rs:333-338, src/lem/store_core.rs:235-241)."""
+    e = _Exprs(oracle)
+    x, plus, mul = e.sym("lurk", "user", "x"), e.sym("lurk", "+"), e.sym("lurk", "*")
+    body = e.lst([plus, e.lst([mul, e.num(3), e.lst([mul, x, x])]), e.lst([plus, e.lst([mul, e.num(9), x]), e.num(2)])])
+    vars_ = e.lst([x])
+    fun = (e.FUN, h(oracle, BN, [*vars_, *body, *e.env0, e.NIL, 0]))
+    comm = e.commit(0, fun)
+    assert comm == GOLDEN["G16"]
+    env = (e.ENV, h(oracle, BN, [e.sym("lurk", "user", "f")[1], fun[0], fun[1], e.env0[1]]))
+    expr = e.lst([e.lst([e.sym("lurk", "open"), e.num(comm)]), e.num(5)])
+    assert e.claim_hash(expr, env, e.num(122), e.env0) == GOLDEN["G17"]
