@@ -128,6 +128,9 @@ int lurk_dag_hash(int field_id, const lurk_dag_node *nodes, size_t n, const uint
  *     is uploaded once into a context; each call streams scalars.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct lurk_msm_ctx lurk_msm_ctx;
+/* bases_affine: n * 64 bytes, x || y per point, (0, 0) = identity.  Coordinates >= p or points off the curve are
+ * rejected with LURK_ERR_RANGE (what the reference's point deserialisation checks before a key is used).  A context
+ * belongs to the device that is current at creation; using it with another device current is LURK_ERR_ARG. */
 int lurk_msm_ctx_create(int curve_id, const uint8_t *bases_affine, size_t n, int fmt, lurk_msm_ctx **out);
 /* bases already on the current device (n * 64 bytes, Montgomery); the context borrows the pointer */
 int lurk_msm_ctx_create_dev(int curve_id, const void *d_bases_mont, size_t n, lurk_msm_ctx **out);

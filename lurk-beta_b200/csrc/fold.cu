@@ -7,6 +7,8 @@
 // iteration (a warp touches 1 KiB contiguous per array), grid = a multiple of the SM count.
 #include "common.cuh"
 
+#include <initializer_list>
+
 namespace lurk {
 
 static inline int stream_grid(size_t n, int block, int per_sm) {
@@ -15,8 +17,9 @@ static inline int stream_grid(size_t n, int block, int per_sm) {
     return (int)(want < cap ? (want ? want : 1) : cap);
 }
 
+// in == out (in place) is allowed and used (dag.cu), hence no __restrict__: each thread reads element i before writing it
 template <class F>
-__global__ void __launch_bounds__(256) convert_kernel(const F *__restrict__ in, size_t n, int to_mont, F *__restrict__ out) {
+__global__ void __launch_bounds__(256) convert_kernel(const F *in, size_t n, int to_mont, F *out) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         F x = load_fe<F>(in + i);
         store_fe(out + i, to_mont ? F::from_canonical(x) : x.to_canonical());
@@ -64,9 +67,9 @@ int check_reduced_accumulate_dev(const void *d_in, size_t n, cudaStream_t s, int
     return LURK_OK;
 }
 
-// out[i] = a[i] + r * b[i]
+// out[i] = a[i] + r * b[i]; out may alias a (the fold updates W1 and E1 in place), so only b is __restrict__
 template <class F>
-__global__ void __launch_bounds__(256) axpy_kernel(const F *__restrict__ a, const F *__restrict__ b, F r, size_t n, F *__restrict__ out) {
+__global__ void __launch_bounds__(256) axpy_kernel(const F *a, const F *__restrict__ b, F r, size_t n, F *out) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         F x = load_fe<F>(a + i), y = load_fe<F>(b + i);
         store_fe(out + i, x + r * y);
@@ -121,8 +124,14 @@ using namespace lurk;
 
 extern "C" {
 
+static int need(size_t n, std::initializer_list<const void *> ptrs) {
+    if (n) for (const void *p : ptrs) if (!p) { set_error("null buffer"); return LURK_ERR_ARG; }
+    return LURK_OK;
+}
+
 int lurk_convert_dev(int field_id, const void *d_in, size_t n, int to_fmt, void *d_out, void *stream) {
     if (to_fmt != LURK_FMT_CANONICAL && to_fmt != LURK_FMT_MONTGOMERY) { set_error("bad format %d", to_fmt); return LURK_ERR_ARG; }
+    LURK_TRY(need(n, {d_in, d_out}));
     LURK_TRY(require_gpu());
     return dispatch_field(field_id, [&](auto f) {
         using F = decltype(f);
@@ -131,6 +140,7 @@ int lurk_convert_dev(int field_id, const void *d_in, size_t n, int to_fmt, void 
 }
 
 int lurk_axpy_dev(int field_id, const void *d_a, const void *d_b, const uint8_t r_mont[32], size_t n, void *d_out, void *stream) {
+    LURK_TRY(need(n, {d_a, d_b, r_mont, d_out}));
     LURK_TRY(require_gpu());
     if (n == 0) return LURK_OK;
     return dispatch_field(field_id, [&](auto f) {
@@ -145,6 +155,7 @@ int lurk_axpy_dev(int field_id, const void *d_a, const void *d_b, const uint8_t 
 
 int lurk_spmv_csr_dev(int field_id, const void *d_row_ptr, const void *d_col, const void *d_val, size_t rows, const void *d_z,
                       void *d_y, void *stream) {
+    LURK_TRY(need(rows, {d_row_ptr, d_z, d_y}));   // col / val may be null for a matrix without non-zeros
     LURK_TRY(require_gpu());
     if (rows == 0) return LURK_OK;
     return dispatch_field(field_id, [&](auto f) {
@@ -158,6 +169,7 @@ int lurk_spmv_csr_dev(int field_id, const void *d_row_ptr, const void *d_col, co
 
 int lurk_cross_term_dev(int field_id, const void *d_az1, const void *d_bz1, const void *d_cz1, const void *d_az2, const void *d_bz2,
                         const void *d_cz2, const uint8_t u1_mont[32], const uint8_t u2_mont[32], size_t n, void *d_t, void *stream) {
+    LURK_TRY(need(n, {d_az1, d_bz1, d_cz1, d_az2, d_bz2, d_cz2, u1_mont, u2_mont, d_t}));
     LURK_TRY(require_gpu());
     if (n == 0) return LURK_OK;
     return dispatch_field(field_id, [&](auto f) {

@@ -94,6 +94,7 @@ int lurk_msm_ctx_precompute(lurk_msm_ctx *ctx) {
 
 int lurk_msm_ctx_clone(lurk_msm_ctx *ctx, lurk_msm_ctx **out) {
     if (!ctx || !out) { set_error("null argument"); return LURK_ERR_ARG; }
+    std::lock_guard<std::mutex> g(ctx->mu);        // a concurrent lurk_msm_ctx_precompute publishes d_table under it
     lurk_msm_ctx *c = new lurk_msm_ctx();
     c->curve_id = ctx->curve_id;
     c->device = ctx->device;
@@ -113,6 +114,8 @@ int lurk_msm_ctx_run(lurk_msm_ctx *ctx, const uint8_t *scalars, size_t n, int fm
     if (n == 0) { memset(out_xyz, 0, 96); return LURK_OK; }
     if (fmt != LURK_FMT_CANONICAL && fmt != LURK_FMT_MONTGOMERY) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
     std::lock_guard<std::mutex> g(ctx->mu);
+    if (ctx->pending) { set_error("a launch is already pending on this context (call lurk_msm_ctx_finish)"); return LURK_ERR_ARG; }
+    LURK_TRY(ctx_check_device(ctx));
     if (ctx->scratch.scalars.bytes < n * 32) LURK_TRY(ctx->scratch.scalars.alloc(n * 32));
     // upload through two pinned staging buffers: the memcpy out of the caller's pageable memory overlaps the DMA
     MsmScratch &S = ctx->scratch;

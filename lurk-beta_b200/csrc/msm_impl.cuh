@@ -411,6 +411,21 @@ __global__ void __launch_bounds__(128) msm_precompute_kernel(const Affine<Fb> *_
     }
 }
 
+// counts affine points (Montgomery coordinates) that are neither the identity encoding (0, 0) nor on y^2 = x^3 + b:
+// the analogue of the on-curve check the reference's point deserialisation performs before a key is used
+template <class Fb>
+__global__ void __launch_bounds__(256) msm_on_curve_kernel(const Affine<Fb> *__restrict__ bases, size_t n, Fb b, int *bad) {
+    int local = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const Affine<Fb> p = load_affine(bases + i);
+        if (p.is_identity()) continue;
+        const Fb lhs = p.y.sqr(), rhs = p.x.sqr() * p.x + b;
+        local += lhs == rhs ? 0 : 1;
+    }
+    local = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(bad, local);
+}
+
 // affine bases: canonical -> Montgomery in place
 template <class Fb>
 __global__ void __launch_bounds__(256) msm_bases_to_mont_kernel(Fb *coords, size_t count) {
@@ -470,6 +485,14 @@ void point_to_bytes(const XYZZ<Fb> &p, int fmt, uint8_t out[96]) {
     memcpy(out, a.x.v, 32); memcpy(out + 32, a.y.v, 32); memcpy(out + 64, one.v, 32);
 }
 
+// a context's buffers live on the device that was current when it was created
+inline int ctx_check_device(const lurk_msm_ctx *ctx) {
+    int dev = -1;
+    LURK_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != ctx->device) { set_error("context belongs to device %d but device %d is current", ctx->device, dev); return LURK_ERR_ARG; }
+    return LURK_OK;
+}
+
 // enqueue the whole pipeline on stream s, ending with the async read-back of the window sums
 template <class C>
 int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cudaStream_t s) {
@@ -477,12 +500,15 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
     using Fs = typename C::Scalar;
     using Pt = XYZZ<Fb>;
     if (ctx->pending) { set_error("a launch is already pending on this context (call lurk_msm_ctx_finish)"); return LURK_ERR_ARG; }
+    LURK_TRY(ctx_check_device(ctx));
     if (!ctx->done) LURK_CUDA_TRY(cudaEventCreateWithFlags(&ctx->done, cudaEventDisableTiming));
     ctx->pending_fmt = fmt;
     ctx->pending_nwin = 0;
     if (n == 0) { ctx->pending = true; return LURK_OK; }
     const bool fixed = ctx->d_table != nullptr;
     MsmPlan P = make_plan(n, Fs::Params::NBITS, fixed ? ctx->fixed_c : 0);
+    // sorted-entry offsets are 32-bit: one launch handles < 2^32 (scalar, window) pairs; larger keys are sharded
+    if ((uint64_t)n * (uint64_t)P.nwin >= (1ull << 32)) { set_error("%zu scalars exceed one launch (shard the commitment key)", n); return LURK_ERR_ARG; }
     MsmScratch &S = ctx->scratch;
     const uint32_t TB = P.total_buckets;
     const uint32_t ntiles = (TB + SCAN_TILE - 1) / SCAN_TILE;
@@ -624,6 +650,16 @@ int ctx_upload(lurk_msm_ctx *ctx, const uint8_t *bases, size_t n, int fmt) {
         LURK_CUDA_TRY(cudaGetLastError());
         LURK_CUDA_TRY(cudaDeviceSynchronize());
     }
+    // curve membership: b = y_G^2 - x_G^3 from the generator
+    const Affine<Fb> g = curve_generator<C>();
+    const Fb b = g.y.sqr() - g.x.sqr() * g.x;
+    DevBuf d_bad;
+    LURK_TRY(d_bad.alloc(sizeof(int)));
+    LURK_CUDA_TRY(cudaMemset(d_bad.p, 0, sizeof(int)));
+    msm_on_curve_kernel<Fb><<<sm_count() * 8, 256>>>((const Affine<Fb> *)ctx->d_bases, n, b, d_bad.as<int>());
+    LURK_CUDA_TRY(cudaGetLastError());
+    LURK_CUDA_TRY(cudaMemcpy(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) { set_error("%d base point(s) are not on the curve", bad); return LURK_ERR_RANGE; }
     return LURK_OK;
 }
 
@@ -631,6 +667,7 @@ int ctx_upload(lurk_msm_ctx *ctx, const uint8_t *bases, size_t n, int fmt) {
 template <class C>
 int msm_precompute(lurk_msm_ctx *ctx) {
     using Fb = typename C::Base;
+    LURK_TRY(ctx_check_device(ctx));
     const int c = fixed_base_window(ctx->n);
     const int nwin = C::Scalar::Params::NBITS / c + 1;
     if (nwin > MSM_MAX_TABLE_WINDOWS || (uint64_t)nwin * ctx->n >= (1ull << 31)) { set_error("commitment key too large for a fixed-base table"); return LURK_ERR_ARG; }

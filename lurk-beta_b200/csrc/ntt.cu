@@ -100,7 +100,6 @@ template <class F>
 struct NttCache {
     std::mutex mu;
     std::map<long, F *> tw;        // key: device * 1024 + log_n * 2 + inverse
-    std::map<long, F *> scratch;   // key: device * 64 + log_n
 };
 
 template <class F>
@@ -128,19 +127,16 @@ static int ntt_run(void *d_data, int log_n, int inverse, cudaStream_t s) {
             F *d = nullptr;
             LURK_CUDA_TRY(cudaMalloc(&d, (n / 2 ? n / 2 : 1) * sizeof(F)));
             ntt_twiddle_kernel<F><<<sm_count() * 4, 256, 0, s>>>(omega, n / 2, d);
-            LURK_CUDA_TRY(cudaGetLastError());
+            cudaError_t e = cudaGetLastError();
+            // the table is shared by every later call on any stream: publish it only once it is complete
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { cudaFree(d); set_error("twiddle generation failed: %s", cudaGetErrorString(e)); return LURK_ERR_CUDA; }
             it = cache.tw.emplace(key, d).first;
         }
         tw = it->second;
-        long skey = (long)dev * 64 + log_n;
-        auto is = cache.scratch.find(skey);
-        if (is == cache.scratch.end()) {
-            F *d = nullptr;
-            LURK_CUDA_TRY(cudaMalloc(&d, n * sizeof(F)));
-            is = cache.scratch.emplace(skey, d).first;
-        }
-        tmp = is->second;
     }
+    // ping-pong buffer from the stream-ordered allocator: concurrent transforms on different streams never share it
+    LURK_CUDA_TRY(cudaMallocAsync((void **)&tmp, n * sizeof(F), s));
     F *a = (F *)d_data;
     const int tile_log = log_n < 10 ? log_n : 10;
     const size_t smem = ((size_t)1 << tile_log) * sizeof(F);
@@ -153,8 +149,10 @@ static int ntt_run(void *d_data, int log_n, int inverse, cudaStream_t s) {
         F ninv = F::from_u64((uint64_t)n).inv();
         ntt_scale_kernel<F><<<grid, 256, 0, s>>>(tmp, n, ninv);
     }
-    LURK_CUDA_TRY(cudaGetLastError());
-    LURK_CUDA_TRY(cudaMemcpyAsync(a, tmp, n * sizeof(F), cudaMemcpyDeviceToDevice, s));
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(a, tmp, n * sizeof(F), cudaMemcpyDeviceToDevice, s);
+    cudaFreeAsync(tmp, s);
+    LURK_CUDA_TRY(e);
     return LURK_OK;
 }
 

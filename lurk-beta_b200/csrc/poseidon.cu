@@ -26,6 +26,11 @@ int bitdecomp_block_host(const uint32_t mod[8]) {
 }
 
 static bool fmt_ok(int fmt) { return fmt == LURK_FMT_CANONICAL || fmt == LURK_FMT_MONTGOMERY; }
+// device-pointer entry points: a null buffer with n > 0 is an argument error, not a kernel fault
+static int need(size_t n, const void *a, const void *b) {
+    if (n && (!a || !b)) { set_error("null buffer"); return LURK_ERR_ARG; }
+    return LURK_OK;
+}
 
 // ---- host-buffer driver shared by the S1/S3 entry points.
 // Small calls: one copy in, one launch, one copy out.  Large calls are cut into chunks that flow through three staging
@@ -162,6 +167,7 @@ int lurk_poseidon_hash_batch_mont(int field_id, int arity, const uint8_t *preima
 int lurk_poseidon_hash_batch_dev(int field_id, int arity, const void *d_preimages, size_t n, void *d_digests, int fmt,
                                  void *stream) {
     if (!fmt_ok(fmt)) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
+    LURK_TRY(need(n, d_preimages, d_digests));
     LURK_TRY(require_gpu());
     return dispatch_field(field_id, [&](auto f) {
         using F = decltype(f);
@@ -211,6 +217,7 @@ int lurk_poseidon_witness_batch(int field_id, int arity, const uint8_t *preimage
 int lurk_poseidon_witness_batch_dev(int field_id, int arity, const void *d_preimages, size_t n, void *d_blocks, int fmt,
                                     void *stream) {
     if (!fmt_ok(fmt)) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
+    LURK_TRY(need(n, d_preimages, d_blocks));
     LURK_TRY(require_gpu());
     return dispatch_field(field_id, [&](auto f) {
         using F = decltype(f);
@@ -222,6 +229,7 @@ int lurk_poseidon_witness_scatter_dev(int field_id, int arity, const void *d_pre
                                       int fmt, void *stream) {
     if (!fmt_ok(fmt)) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
     if (n && !d_offsets) { set_error("null offsets"); return LURK_ERR_ARG; }
+    LURK_TRY(need(n, d_preimages, d_base));
     LURK_TRY(require_gpu());
     return dispatch_field(field_id, [&](auto f) {
         using F = decltype(f);
@@ -232,6 +240,7 @@ int lurk_bitdecomp_witness_scatter_dev(int field_id, const void *d_values, size_
                                        void *stream) {
     if (!fmt_ok(fmt)) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
     if (n && !d_offsets) { set_error("null offsets"); return LURK_ERR_ARG; }
+    LURK_TRY(need(n, d_values, d_base));
     LURK_TRY(require_gpu());
     if (n == 0) return LURK_OK;
     int blk = (int)lurk_bitdecomp_witness_block(field_id);
@@ -254,6 +263,7 @@ size_t lurk_bitdecomp_witness_block(int field_id) {
 }
 int lurk_bitdecomp_witness_batch_dev(int field_id, const void *d_values, size_t n, void *d_blocks, int fmt, void *stream) {
     if (!fmt_ok(fmt)) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
+    LURK_TRY(need(n, d_values, d_blocks));
     LURK_TRY(require_gpu());
     if (n == 0) return LURK_OK;
     int blk = (int)lurk_bitdecomp_witness_block(field_id);
@@ -264,6 +274,7 @@ int lurk_bitdecomp_witness_batch_dev(int field_id, const void *d_values, size_t 
 }
 int lurk_bitdecomp_witness_batch(int field_id, const uint8_t *values, size_t n, uint8_t *blocks, int fmt) {
     if (!fmt_ok(fmt)) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
+    LURK_TRY(need(n, values, blocks));
     LURK_TRY(require_gpu());
     if (n == 0) return LURK_OK;
     size_t blk = lurk_bitdecomp_witness_block(field_id);

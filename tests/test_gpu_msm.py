@@ -66,6 +66,32 @@ def test_msm_errors(L, oracle, spec):
     assert e.value.code == L._capi.ERR_RANGE
 
 
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+def test_off_curve_and_unreduced_bases_rejected(L, oracle, spec, curve):
+    """a commitment key is validated at upload: coordinates < p and y^2 = x^3 + b ((0, 0) = identity is allowed)"""
+    good = oracle.gen_bases(curve, 64)
+    good[64 * 7:64 * 8] = 0
+    L.CommitmentKey(curve, good)                              # accepted
+    bad = good.copy()
+    bad[64 * 33 + 32] ^= 1                                    # y of base 33 off by one bit: not on the curve
+    with pytest.raises(L.LurkError, match="not on the curve") as e:
+        L.CommitmentKey(curve, bad)
+    assert e.value.code == L._capi.ERR_RANGE
+    bad = good.copy()
+    bad[64 * 5:64 * 5 + 32] = pack([spec.FIELD_MODULUS[spec.CURVES[curve]["base"]]])   # x = p
+    with pytest.raises(L.LurkError) as e:
+        L.CommitmentKey(curve, bad)
+    assert e.value.code == L._capi.ERR_RANGE
+    # Montgomery-format keys go through the same check
+    pb = spec.FIELD_MODULUS[spec.CURVES[curve]["base"]]
+    R = (1 << 256) % pb
+    gm = pack([x * R % pb for x in ints(good)])
+    L.CommitmentKey(curve, gm, fmt=L.FMT_MONTGOMERY)
+    gm[64 * 2] ^= 1
+    with pytest.raises(L.LurkError, match="not on the curve"):
+        L.CommitmentKey(curve, gm, fmt=L.FMT_MONTGOMERY)
+
+
 def test_msm_montgomery_format(L, oracle, spec):
     curve, n = 0, 500
     C = spec.CURVES[curve]
