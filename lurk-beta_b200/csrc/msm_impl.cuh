@@ -37,16 +37,18 @@ static constexpr uint32_t KEY_NONE = 0xffffffffu;
 struct MsmPlan {
     int c = 0;             // window bits
     int nwin = 0;          // windows
-    uint32_t nb = 0;       // buckets per window = 2^(c-1)
+    uint32_t nb = 0;       // buckets per bucket set = 2^(c-1)
     uint32_t total_buckets = 0;
     uint32_t seg = 0;      // sorted entries per level-1 thread
     uint32_t t1 = 0;       // level-1 threads = partial slots
-    uint32_t chunk = 0;    // buckets per bucket-reduce thread
-    // fixed-base mode (window multiples of every base precomputed): one shared bucket set of 2^(c-1) buckets, cut into
-    // `vwin` virtual windows of `nb` buckets for the reduction; entries address table[w * key_n + i]
+    // fixed-base mode (window multiples of every base precomputed): all windows share ONE bucket set of 2^(c-1) buckets;
+    // entries address table[w * key_n + i]
     bool fixed = false;
-    uint32_t vwin = 0;
+    // bucket reduction (see msm_chunk_kernel): rwin bucket sets of nb buckets, chunks of K, G = nb / K chunks per set,
+    // nq = 1 + log2 G sums per set, each cut into SL slices of `slice` chunks
+    uint32_t rwin = 0, K = 0, G = 0, nq = 0, SL = 0, slice = 0;
 };
+static constexpr uint32_t MSM_MAX_RESULT_POINTS = 512;    // rwin * nq <= 64 * 1 .. 13 * 17: read back per commitment
 
 inline int fixed_base_window(size_t key_n) {
     int lg = 0;
@@ -60,17 +62,16 @@ inline MsmPlan make_plan(size_t n, int scalar_bits, int fixed_c = 0) {
     while (((size_t)1 << (lg + 1)) <= n) lg++;
     p.c = fixed_c ? fixed_c : std::min(20, std::max(4, lg - 5));
     p.nwin = scalar_bits / p.c + 1;
-    if (fixed_c) {
-        p.fixed = true;
-        const uint32_t all = 1u << (p.c - 1);
-        p.nb = std::min<uint32_t>(all, 1u << 15);
-        p.vwin = all / p.nb;
-        p.total_buckets = all;
-    } else {
-        p.nb = 1u << (p.c - 1);
-        p.vwin = (uint32_t)p.nwin;
-        p.total_buckets = p.nb * (uint32_t)p.nwin;
-    }
+    p.fixed = fixed_c != 0;
+    p.nb = 1u << (p.c - 1);
+    p.rwin = p.fixed ? 1u : (uint32_t)p.nwin;
+    p.total_buckets = p.nb * p.rwin;
+    p.K = std::min<uint32_t>(8, p.nb);
+    p.G = p.nb / p.K;
+    p.nq = 1;
+    while ((1u << (p.nq - 1)) < p.G) p.nq++;
+    p.SL = std::min<uint32_t>(32, std::max<uint32_t>(1, p.G / 2048));
+    p.slice = p.G / p.SL;
     size_t cap = n * (size_t)p.nwin;
     size_t want_threads = (size_t)sm_count() * 1024;
     size_t seg = (cap + want_threads - 1) / want_threads;
@@ -78,7 +79,6 @@ inline MsmPlan make_plan(size_t n, int scalar_bits, int fixed_c = 0) {
     p.seg = (uint32_t)std::min<size_t>(seg_cap, std::max<size_t>(8, seg));
     p.t1 = (uint32_t)((cap + p.seg - 1) / p.seg);
     if (p.t1 == 0) p.t1 = 1;
-    p.chunk = std::min<uint32_t>(16, p.nb);
     return p;
 }
 
@@ -338,41 +338,90 @@ __global__ void __launch_bounds__(128) msm_partial_warp_kernel(const uint32_t *_
     if (first_key == KEY_NONE && lane == 0 && !last_level) keys_out[gw] = KEY_NONE;
 }
 
-// per chunk of `chunk` buckets [b0, b0+chunk) of window w:  sum_b (b+1) B_b = tri + b0 * S
+// ---- bucket reduction: R_w = sum_b (b + 1) B_{w,b} per window, in three short, wide kernels.
+// With chunks of K buckets (g = chunk index, G = buckets per window / K):
+//     R_w = sum_g tri_g + K * sum_g g * run_g,   tri_g = sum_j (j + 1) B_{gK + j},   run_g = sum_j B_{gK + j}
+// and the weighted sum over chunks is taken bit by bit: sum_g g run_g = sum_k 2^k S_k, S_k = sum of run_g over the g with
+// bit k set.  Every S_k (and the plain sum of the tri_g) is an ordinary tree reduction, so nothing on this path is longer
+// than 2K + a few dozen dependent point additions and no scalar multiplication is needed; the final Horner over the
+// (1 + log2 G) sums per window runs on the host in msm_finish.
+
+// level 0: one thread per chunk of K buckets
 template <class Fb>
-__global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(const XYZZ<Fb> *__restrict__ bucket_acc, uint32_t nb, uint32_t chunk,
-                                                                uint32_t nchunks_total, XYZZ<Fb> *__restrict__ chunk_out,
-                                                                XYZZ<Fb> *__restrict__ chunk_sum_out) {
+__global__ void __launch_bounds__(128) msm_chunk_kernel(const XYZZ<Fb> *__restrict__ bucket_acc, uint32_t K, uint32_t nchunks_total,
+                                                        XYZZ<Fb> *__restrict__ tri_out, XYZZ<Fb> *__restrict__ run_out) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nchunks_total) return;
-    const uint32_t per_win = nb / chunk;
-    const uint32_t w = g / per_win, ch = g % per_win;
-    const uint32_t b0 = ch * chunk;
-    const XYZZ<Fb> *B = bucket_acc + (size_t)w * nb + b0;
+    const XYZZ<Fb> *B = bucket_acc + (size_t)g * K;
     XYZZ<Fb> run = XYZZ<Fb>::identity(), tri = XYZZ<Fb>::identity();
-    for (int b = (int)chunk - 1; b >= 0; b--) {
+    for (int b = (int)K - 1; b >= 0; b--) {
         run.add(load_xyzz(B + b));
         tri.add(run);
     }
-    if (b0) tri.add(run.mul_u32(b0));
-    store_xyzz(chunk_out + g, tri);
-    if (chunk_sum_out) store_xyzz(chunk_sum_out + g, run);   // plain sum of the chunk (fixed-base mode)
+    store_xyzz(tri_out + g, tri);
+    store_xyzz(run_out + g, run);
 }
 
-// one CTA per window: sum of its chunk results
+// level 1: block (sl, q, w) sums, over slice sl of window w's G chunks, the tri_g (q = 0) or the run_g with bit q-1 of g
+// set (q >= 1).  out[((w * nq) + q) * SL + sl].  Slices are aligned powers of two, so "bit k set" is enumerated directly.
 template <class Fb>
-__global__ void __launch_bounds__(256) msm_window_sum_kernel(const XYZZ<Fb> *__restrict__ chunk_in, uint32_t per_win, XYZZ<Fb> *__restrict__ win_out) {
+__global__ void __launch_bounds__(256) msm_bitsum_kernel(const XYZZ<Fb> *__restrict__ tri, const XYZZ<Fb> *__restrict__ run, uint32_t G,
+                                                         uint32_t slice, XYZZ<Fb> *__restrict__ out) {
     __shared__ XYZZ<Fb> sm[256];
-    const uint32_t w = blockIdx.x, tid = threadIdx.x;
+    const uint32_t sl = blockIdx.x, q = blockIdx.y, w = blockIdx.z, tid = threadIdx.x;
+    const uint32_t SL = gridDim.x, nq = gridDim.y;
+    const size_t base = (size_t)w * G + (size_t)sl * slice;
     XYZZ<Fb> acc = XYZZ<Fb>::identity();
-    for (uint32_t i = tid; i < per_win; i += blockDim.x) acc.add(load_xyzz(chunk_in + (size_t)w * per_win + i));
+    if (q == 0) {
+        for (uint32_t i = tid; i < slice; i += blockDim.x) acc.add(load_xyzz(tri + base + i));
+    } else {
+        const uint32_t k = q - 1;
+        if (slice > (1u << k)) {
+            const uint32_t low = (1u << k) - 1;
+            for (uint32_t j = tid; j < slice / 2; j += blockDim.x) {
+                const uint32_t local = ((j >> k) << (k + 1)) | (1u << k) | (j & low);
+                acc.add(load_xyzz(run + base + local));
+            }
+        } else if (((sl * slice) >> k) & 1u) {       // bit k is constant over this slice
+            for (uint32_t i = tid; i < slice; i += blockDim.x) acc.add(load_xyzz(run + base + i));
+        }
+    }
     sm[tid] = acc;
     __syncthreads();
     for (uint32_t stride = blockDim.x / 2; stride > 0; stride >>= 1) {
         if (tid < stride) { XYZZ<Fb> a = sm[tid]; a.add(sm[tid + stride]); sm[tid] = a; }
         __syncthreads();
     }
-    if (tid == 0) store_xyzz(win_out + w, sm[0]);
+    if (tid == 0) store_xyzz(out + ((size_t)w * nq + q) * SL + sl, sm[0]);
+}
+
+template <class Fb>
+__device__ __forceinline__ XYZZ<Fb> shfl_xor_xyzz(const XYZZ<Fb> &p, int d) {
+    XYZZ<Fb> r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.x.v[i] = __shfl_xor_sync(0xffffffffu, p.x.v[i], d);
+        r.y.v[i] = __shfl_xor_sync(0xffffffffu, p.y.v[i], d);
+        r.zz.v[i] = __shfl_xor_sync(0xffffffffu, p.zz.v[i], d);
+        r.zzz.v[i] = __shfl_xor_sync(0xffffffffu, p.zzz.v[i], d);
+    }
+    return r;
+}
+
+// level 2 (only when a window was cut into SL > 1 slices): one warp per (w, q) adds the SL <= 32 slice sums
+template <class Fb>
+__global__ void __launch_bounds__(128) msm_slice_sum_kernel(const XYZZ<Fb> *__restrict__ in, uint32_t SL, uint32_t count,
+                                                            XYZZ<Fb> *__restrict__ out) {
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= count) return;                           // whole warps exit together
+    XYZZ<Fb> pt = XYZZ<Fb>::identity();
+    if (lane < SL) pt = load_xyzz(in + (size_t)gw * SL + lane);
+#pragma unroll 1
+    for (int d = 16; d > 0; d >>= 1) {
+        const XYZZ<Fb> p2 = shfl_xor_xyzz(pt, d);
+        if ((uint32_t)d < SL) pt.add(p2);             // uniform per warp: lanes >= SL hold the identity anyway
+    }
+    if (lane == 0) store_xyzz(out + gw, pt);
 }
 
 // Fixed-base table: table[w * n + i] = 2^(c w) * bases[i], affine.  One thread per base walks the windows with c
@@ -435,7 +484,7 @@ __global__ void __launch_bounds__(256) msm_bases_to_mont_kernel(Fb *coords, size
 
 // ----------------------------------------------------------------------------- context
 struct MsmScratch {
-    DevBuf counts, offsets, tiles, sorted, buckets, pkey[2], ppt[2], chunks, chunk_sums, wins, scalars;
+    DevBuf counts, offsets, tiles, sorted, buckets, pkey[2], ppt[2], chunks, chunk_sums, slices, wins, scalars;
     void *h_wins = nullptr;   // pinned
     void *h_stage[2] = {nullptr, nullptr};          // pinned staging for host-buffer scalars
     cudaEvent_t stage_done[2] = {nullptr, nullptr};
@@ -469,7 +518,7 @@ struct lurk_msm_ctx {
     bool pending = false;
     int pending_fmt = 0, pending_c = 0, pending_nwin = 0;
     bool pending_fixed = false;
-    uint32_t pending_vwin = 0, pending_nb = 0;
+    uint32_t pending_nq = 0, pending_K = 0;
     cudaEvent_t done = nullptr;
 };
 
@@ -525,10 +574,12 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
         size_t t2 = ((size_t)P.t1 + 7) / 8;
         LURK_TRY(ensure(S.pkey[1], t2 * sizeof(uint32_t)));
         LURK_TRY(ensure(S.ppt[1], t2 * sizeof(Pt)));
-        LURK_TRY(ensure(S.chunks, (size_t)(TB / P.chunk) * sizeof(Pt)));
-        if (fixed) LURK_TRY(ensure(S.chunk_sums, (size_t)(TB / P.chunk) * sizeof(Pt)));
-        LURK_TRY(ensure(S.wins, 128 * sizeof(Pt)));
-        if (!S.h_wins) LURK_CUDA_TRY(cudaMallocHost(&S.h_wins, 128 * sizeof(Pt)));
+        const size_t nchunks_all = (size_t)P.rwin * P.G;
+        LURK_TRY(ensure(S.chunks, nchunks_all * sizeof(Pt)));          // tri_g
+        LURK_TRY(ensure(S.chunk_sums, nchunks_all * sizeof(Pt)));      // run_g
+        LURK_TRY(ensure(S.slices, (size_t)P.rwin * P.nq * P.SL * sizeof(Pt)));
+        LURK_TRY(ensure(S.wins, MSM_MAX_RESULT_POINTS * sizeof(Pt)));
+        if (!S.h_wins) LURK_CUDA_TRY(cudaMallocHost(&S.h_wins, MSM_MAX_RESULT_POINTS * sizeof(Pt)));
     }
     if (ntiles > 4096) { set_error("bucket table too large for the scan"); return LURK_ERR_ARG; }
     uint32_t *counts = S.counts.as<uint32_t>();
@@ -581,22 +632,27 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
         count = warps;
         cur ^= 1;
     }
-    const uint32_t nchunks = TB / P.chunk;
-    msm_bucket_reduce_kernel<Fb><<<(nchunks + 127) / 128, 128, 0, s>>>(buckets, P.nb, P.chunk, nchunks, S.chunks.as<Pt>(),
-                                                                       fixed ? S.chunk_sums.as<Pt>() : nullptr);
-    msm_window_sum_kernel<Fb><<<P.vwin, 256, 0, s>>>(S.chunks.as<Pt>(), P.nb / P.chunk, S.wins.as<Pt>());
+    // bucket reduction: chunk sums, per-bit tree sums, (slice sums); the host finishes with a Horner over nq points per set
+    const uint32_t nchunks = P.rwin * P.G, nres = P.rwin * P.nq;
+    if (nres > MSM_MAX_RESULT_POINTS) { set_error("internal: %u result points", nres); return LURK_ERR_ARG; }
+    msm_chunk_kernel<Fb><<<(nchunks + 127) / 128, 128, 0, s>>>(buckets, P.K, nchunks, S.chunks.as<Pt>(), S.chunk_sums.as<Pt>());
+    msm_bitsum_kernel<Fb><<<dim3(P.SL, P.nq, P.rwin), 256, 0, s>>>(S.chunks.as<Pt>(), S.chunk_sums.as<Pt>(), P.G, P.slice,
+                                                                  P.SL > 1 ? S.slices.as<Pt>() : S.wins.as<Pt>());
     launches += 2;
-    if (fixed) { msm_window_sum_kernel<Fb><<<P.vwin, 256, 0, s>>>(S.chunk_sums.as<Pt>(), P.nb / P.chunk, S.wins.as<Pt>() + 64); launches++; }
+    if (P.SL > 1) {
+        msm_slice_sum_kernel<Fb><<<(nres * 32 + 127) / 128, 128, 0, s>>>(S.slices.as<Pt>(), P.SL, nres, S.wins.as<Pt>());
+        launches++;
+    }
     ctx->last_launches = launches;
     LURK_CUDA_TRY(cudaGetLastError());
-    LURK_CUDA_TRY(cudaMemcpyAsync(S.h_wins, S.wins.p, (size_t)(fixed ? 128 : P.vwin) * sizeof(Pt), cudaMemcpyDeviceToHost, s));
+    LURK_CUDA_TRY(cudaMemcpyAsync(S.h_wins, S.wins.p, (size_t)nres * sizeof(Pt), cudaMemcpyDeviceToHost, s));
     LURK_CUDA_TRY(cudaEventRecord(ctx->done, s));
     ctx->pending = true;
     ctx->pending_c = P.c;
     ctx->pending_nwin = P.nwin;
     ctx->pending_fixed = fixed;
-    ctx->pending_vwin = P.vwin;
-    ctx->pending_nb = P.nb;
+    ctx->pending_nq = P.nq;
+    ctx->pending_K = P.K;
     return LURK_OK;
 }
 
@@ -610,20 +666,24 @@ int msm_finish(lurk_msm_ctx *ctx, uint8_t out[96]) {
     if (ctx->pending_nwin == 0) { memset(out, 0, 96); return LURK_OK; }
     LURK_CUDA_TRY(cudaEventSynchronize(ctx->done));
     if (ctx->profile) cudaEventElapsedTime(&ctx->last_accumulate_ms, ctx->ev0, ctx->ev1);
-    const Pt *w = reinterpret_cast<const Pt *>(ctx->scratch.h_wins);
+    const Pt *h = reinterpret_cast<const Pt *>(ctx->scratch.h_wins);
+    const uint32_t nq = ctx->pending_nq;
+    // bucket set r: R_r = T + K * sum_k 2^k S_k with (T, S_0, .., S_{nq-2}) = h[r * nq ..]  (see msm_chunk_kernel)
+    auto bucket_set = [&](uint32_t r) {
+        const Pt *q = h + (size_t)r * nq;
+        Pt a = Pt::identity();
+        for (uint32_t k = nq - 1; k >= 1; k--) { a = a.dbl(); a.add(q[k]); }
+        for (uint32_t m = ctx->pending_K; m > 1; m >>= 1) a = a.dbl();
+        a.add(q[0]);
+        return a;
+    };
     Pt acc = Pt::identity();
     if (ctx->pending_fixed) {
-        // shared bucket set cut into virtual windows: sum_v R_v + nb * sum_v v S_v; the weighted sum is a running sum
-        // over the (<= 16) virtual windows, nb is a power of two
-        Pt run = Pt::identity(), wsum = Pt::identity();
-        for (uint32_t v = ctx->pending_vwin; v-- > 1;) { run.add(w[64 + v]); wsum.add(run); }
-        for (uint32_t b = ctx->pending_nb; b > 1; b >>= 1) wsum = wsum.dbl();
-        for (uint32_t v = 0; v < ctx->pending_vwin; v++) acc.add(w[v]);
-        acc.add(wsum);
+        acc = bucket_set(0);                       // the table already carries the 2^(c w) factors
     } else {
         for (int i = ctx->pending_nwin - 1; i >= 0; i--) {
             for (int d = 0; d < ctx->pending_c; d++) acc = acc.dbl();
-            acc.add(w[i]);
+            acc.add(bucket_set((uint32_t)i));
         }
     }
     point_to_bytes(acc, ctx->pending_fmt, out);
