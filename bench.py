@@ -244,12 +244,6 @@ class FoldStepGPU:
         b = i % nb
         before = self.stage_inputs if staged else None
         kA = self.pipe.launches_A
-        while self.prefetched < i:                               # first step only: stage A of this very step
-            self.prefetched += 1
-            self.pipe.stage_a(self.prefetched % nb, self.slot_batches[self.prefetched % nb], before)
-        # the sequential chain first: the host needs ~0.3 ms to enqueue a step's ~100 launches, and whatever is enqueued
-        # before Az1 / cross term / commit(T) delays the chain by that much (profiles/r1_step_timeline.txt)
-        self.pipe.stage_b_launch(b)
         while self.prefetched < i + PREFETCH_DEPTH:              # keep stage A PREFETCH_DEPTH steps ahead
             self.prefetched += 1
             self.pipe.stage_a(self.prefetched % nb, self.slot_batches[self.prefetched % nb], before)
@@ -257,7 +251,7 @@ class FoldStepGPU:
         # secondary circuit (Grumpkin): two small commitments, independent of the primary fold
         self.ck2.launch_device(self.W_sec.data_ptr(), SECONDARY_N, fmt=M, stream=self.sS.cuda_stream)
         self.ck2b.launch_device(self.T_sec.data_ptr(), SECONDARY_N, fmt=M, stream=self.sS.cuda_stream)
-        cw, ct = self.pipe.stage_b_collect(b, self.challenge)
+        cw, ct = self.pipe.stage_b(b, self.challenge)
         self.ck2.finish()
         self.ck2b.finish()
         self.step_index = i + 1
