@@ -1,4 +1,4 @@
-"""CPU tests of the store mirror's HOST logic (interning, children-first flattening into lurk_dag_node records, digest
+"""CPU tests of the HOST logic of the store, trie and slot mirrors (interning, children-first flattening into lurk_dag_node
 tables, commitments) against the reference's goldens.  There is no GPU here, so the two device entry points the mirror
 calls are replaced -- in this test module only -- by a stand-in that hands the very same buffers to the oracle; what
 is under test is everything the mirror does before and after that call.  The same expressions run against the real
@@ -33,12 +33,31 @@ class _OracleBackedLib:
         self._view(out, n * 32)[:] = self.o.poseidon_hash_batch(field, arity, self._view(pre, n * arity * 32))
         return 0
 
+    def lurk_poseidon_witness_batch(self, field, arity, pre, n, blocks, fmt):
+        assert fmt == 0
+        w = self.o.poseidon_witness_batch(field, arity, self._view(pre, n * arity * 32))
+        self._view(blocks, w.size)[:] = w
+        return 0
+
+    def lurk_bitdecomp_witness_batch(self, field, vals, n, blocks, fmt):
+        assert fmt == 0
+        w = self.o.bitdecomp_witness_batch(field, self._view(vals, n * 32))
+        self._view(blocks, w.size)[:] = w
+        return 0
+
+    def __getattr__(self, name):
+        # host-only entry points (block sizes, constants) need no GPU: the real library answers them
+        if name in ("lurk_poseidon_witness_block", "lurk_bitdecomp_witness_block", "lurk_poseidon_constants", "lurk_last_error"):
+            return getattr(self._real, name)
+        raise AttributeError(f"{name}: a device entry point this CPU test does not stand in for")
+
 
 @pytest.fixture()
 def HL(monkeypatch, oracle):
     import lurk_beta_b200 as L
     from lurk_beta_b200 import _capi
     fake = _OracleBackedLib(oracle)
+    fake._real = _capi.lib()
     monkeypatch.setattr(_capi, "lib", lambda: fake)
     L._fake = fake
     return L
@@ -77,3 +96,87 @@ def test_hydrate_queue_matches_on_demand_hashing(HL):
     pa, pb = mk(a), mk(b)
     a.s.hydrate_z_cache()
     assert not a.s.dehydrated and a.s.z_cache[pa[1]] == b.s.hash_ptr(pb)[1]
+
+
+def test_random_dags_match_recursive_hashing(HL, oracle):
+    """random hash-consed DAGs (all five node kinds, shared sub-terms, several hydration calls so that later batches refer to
+    earlier digests) through the mirror's flattening == plain recursive hashing with the oracle"""
+    import random
+    from util import ints, pack
+    rng = random.Random(0x6c75726b)
+    H = lambda pre: ints(oracle.poseidon_hash_batch(0, len(pre), pack(pre)))[0]
+    for trial in range(4):
+        s = HL.StoreCore(HL.FIELD_BN254_FR)
+        ptrs, want = [], {}                      # ptr -> digest by direct recursion
+
+        def digest(p):
+            return want[p] if p[1][0] != "atom" else s.fetch_digest(p[1][1])
+
+        for i in range(12):
+            v = rng.randrange(1 << 200)
+            p = s.intern_atom(rng.randrange(15), v)
+            ptrs.append(p)
+        for step in range(120):
+            kind = rng.choice(["tuple2", "tuple3", "tuple4", "compact"])
+            tag = rng.randrange(15)
+            k = {"tuple2": 2, "tuple3": 3, "tuple4": 4, "compact": 3}[kind]
+            ch = [rng.choice(ptrs[-30:] if rng.random() < 0.7 else ptrs) for _ in range(k)]
+            p = getattr(s, "intern_" + kind)(ch, tag)
+            if kind == "compact":
+                want[p] = H([digest(ch[0]), ch[1][0], digest(ch[1]), digest(ch[2])])
+            else:
+                want[p] = H([x for c in ch for x in (c[0], digest(c))])
+            ptrs.append(p)
+            if step % 37 == 36:                  # hydrate part-way: later nodes refer to already cached digests
+                s.hydrate_z_cache()
+        probe = [p for p in ptrs if p[1][0] != "atom"]
+        rng.shuffle(probe)
+        for p in probe[:40]:
+            assert s.hash_ptr(p) == (p[0], want[p])
+        s.hydrate_z_cache()
+        assert all(s.z_cache[p[1]] == want[p] for p in probe)
+        # commitments on top (hash3 of secret, tag, digest)
+        p = probe[0]
+        assert s.hide(77, p) == H([77, p[0], want[p]])
+
+
+def test_trie_mirror_goldens_and_lookup_witnesses(HL, oracle):
+    """trie coprocessor mirror (src/coprocessor/trie/mod.rs): empty roots G1..G5, root after insert G10, lookups, and the 85
+    arity-8 slot witnesses of one lookup circuit handed over as ONE batch"""
+    from util import pack
+    pc = HL.PoseidonCache(HL.FIELD_BN254_FR)
+    small = HL.Trie(pc, 8, 3)
+    assert [small.empty_root_for_height(h) for h in (1, 2, 3)] == [GOLDEN["G1"], GOLDEN["G2"], GOLDEN["G3"]]
+    assert small.path(500) == [7, 6, 4]                                  # test_path, trie/mod.rs
+    t = HL.StandardTrie(pc)
+    assert t.empty_root() == GOLDEN["G5"]
+    assert t.lookup(123) is None
+    assert t.insert(123, 456) and t.root == GOLDEN["G10"]
+    assert t.lookup(123) == 456 and t.lookup(124) is None
+    assert not t.insert(123, 456)                                        # same value: root unchanged
+    w = t.lookup_circuit_witnesses(123)
+    pre = pack([x for p in t.prove_lookup_at_path(t.path(123)) for x in p])
+    assert w.size == 85 * 396 * 32 and np.array_equal(w, oracle.poseidon_witness_batch(0, 8, pre))
+    with pytest.raises(KeyError, match="MissingPreimage"):
+        HL.StandardTrie(pc, root=12345).lookup(1)
+
+
+def test_generate_slots_witnesses_order_and_dummies(HL, oracle):
+    """frame order is preserved, one batch per slot type, all `None` slots of a type share the zero-preimage witness
+    (src/lem/multiframe.rs:520-592)"""
+    from util import ints, pack
+    S = HL.SlotType
+    slots = [(S.Hash4, [1, 2, 3, 4]), (S.Hash4, None), (S.Hash8, list(range(8))), (S.Commitment, [9, 4, 7]), (S.BitDecomp, [5]),
+             (S.Hash4, None), (S.Hash8, None), (S.BitDecomp, None), (S.Hash4, [4, 3, 2, 1])]
+    got = HL.generate_slots_witnesses(0, slots)
+    assert len(got) == len(slots)
+    for (st, pre), blk in zip(slots, got):
+        a = st.preimg_size()
+        row = pack(pre if pre is not None else [0] * a)
+        want = oracle.bitdecomp_witness_batch(0, row) if st is S.BitDecomp else oracle.poseidon_witness_batch(0, a, row)
+        assert np.array_equal(blk, want), (st, pre)
+        assert blk.size == HL.compute_witness_size(st, 0) * 32
+    assert got[1] is not got[0] and np.array_equal(got[1], got[5])
+    assert ints(got[0])[:4] == [1, 2, 3, 4] and ints(got[8])[:4] == [4, 3, 2, 1]     # block = preimage | aux | digest
+    with pytest.raises(ValueError):
+        HL.generate_slots_witnesses(0, [(S.Hash4, [1, 2, 3])])
