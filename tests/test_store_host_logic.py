@@ -1,6 +1,6 @@
 """CPU tests of the HOST logic of the store, trie and slot mirrors (interning, children-first flattening into lurk_dag_node
-tables, commitments) against the reference's goldens.  There is no GPU here, so the two device entry points the mirror
-calls are replaced -- in this test module only -- by a stand-in that hands the very same buffers to the oracle; what
+tables, commitments) against the reference's goldens.  There is no GPU here, so the device entry points the mirrors
+call are replaced -- in this test module only -- by a stand-in that hands the very same buffers to the oracle; what
 is under test is everything the mirror does before and after that call.  The same expressions run against the real
 library in tests/test_gpu_dag_fold.py."""
 import ctypes as C
