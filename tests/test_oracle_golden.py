@@ -269,3 +269,40 @@ def test_functional_commitment_demo(oracle):
     env = (e.ENV, h(oracle, BN, [e.sym("lurk", "user", "f")[1], fun[0], fun[1], e.env0[1]]))
     expr = e.lst([e.lst([e.sym("lurk", "open"), e.num(comm)]), e.num(5)])
     assert e.claim_hash(expr, env, e.num(122), e.env0) == GOLDEN["G17"]
+
+
+def _chained_counter(e, oracle):
+    """the closures of demo/chained-functional-commitment.lurk.  `(add c)` is an undersaturated call of the two-argument
+    recursive closure: Fun((x), body, env) with env = {counter -> c} on top of {add -> Rec} (src/lem/eval.rs:1470-1500);
+    looking `add` up turns the Rec (the Fun's digest under tag 13, :1511-1517) back into a Fun whose environment binds
+    `add` again (:1084-1090).  Returns head(c) -> commitment digest."""
+    REC, sym = 13, e.sym
+    counter, x, add = sym("lurk", "user", "counter"), sym("lurk", "user", "x"), sym("lurk", "user", "add")
+    let, plus, cons_, commit = sym("lurk", "let"), sym("lurk", "+"), sym("lurk", "cons"), sym("lurk", "commit")
+    body = e.lst([let, e.lst([e.lst([counter, e.lst([plus, counter, x])])]),
+                  e.lst([cons_, counter, e.lst([commit, e.lst([add, counter])])])])
+    foo = (e.NIL, 0)
+    cons4 = lambda a, b, c, d: h(oracle, BN, [*a, *b, *c, *d])
+    push = lambda s, v, env: (e.ENV, h(oracle, BN, [s[1], v[0], v[1], env[1]]))         # compact node
+    rec = (REC, cons4(e.lst([counter, x]), body, e.env0, foo))
+    rec_env = push(add, rec, e.env0)
+    return lambda c: e.commit(0, (e.FUN, cons4(e.lst([x]), body, push(counter, e.num(c), rec_env), foo)))
+
+
+def test_chained_functional_commitment_demo(oracle):
+    """G18..G23 (demo/chained-functional-commitment.lurk): three links of the chain and the claims of their proofs; the
+    input expression of a chain/call claim is ((open <Num hash>) arg) whether the head was given as a number or as a
+    (comm ..) literal (src/cli/repl/meta_cmd.rs:538-539), the output is (total . (comm <next head>)) with Comm = tag 8."""
+    COMM = 8
+    e = _Exprs(oracle)
+    head = _chained_counter(e, oracle)
+    c0, c1, c2, c3 = head(0), head(9), head(21), head(35)
+    assert (c0, c1, c2) == (GOLDEN["G18"], GOLDEN["G19"], GOLDEN["G20"])
+
+    def claim(cin, arg, total, cout):
+        expr = e.lst([e.lst([e.sym("lurk", "open"), e.num(cin)]), e.num(arg)])
+        return e.claim_hash(expr, e.env0, e.cons(e.num(total), (COMM, cout)), e.env0)
+
+    assert claim(c0, 9, 9, c1) == GOLDEN["G21"]
+    assert claim(c1, 12, 21, c2) == GOLDEN["G22"]
+    assert claim(c2, 14, 35, c3) == GOLDEN["G23"]

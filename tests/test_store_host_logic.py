@@ -180,3 +180,29 @@ def test_generate_slots_witnesses_order_and_dummies(HL, oracle):
     assert ints(got[0])[:4] == [1, 2, 3, 4] and ints(got[8])[:4] == [4, 3, 2, 1]     # block = preimage | aux | digest
     with pytest.raises(ValueError):
         HL.generate_slots_witnesses(0, [(S.Hash4, [1, 2, 3])])
+
+
+def test_chained_commitment_goldens_through_store_flattening(HL):
+    """G18..G21 through the store mirror: nested compact Env nodes, a Rec (tuple4 digest under another tag) and a Comm-tagged
+    output, hashed in a handful of lurk_dag_hash calls that reuse earlier digests"""
+    REC, COMM = 13, 8
+    e = _StoreExprs(HL)
+    s = e.s
+    counter, x, add = e.sym("lurk", "user", "counter"), e.sym("lurk", "user", "x"), e.sym("lurk", "user", "add")
+    let, plus, cons_, commit = e.sym("lurk", "let"), e.sym("lurk", "+"), e.sym("lurk", "cons"), e.sym("lurk", "commit")
+    body = e.lst([let, e.lst([e.lst([counter, e.lst([plus, counter, x])])]),
+                  e.lst([cons_, counter, e.lst([commit, e.lst([add, counter])])])])
+    foo = s.intern_atom(e.NIL, 0)
+    fun2 = s.intern_tuple4([e.lst([counter, x]), body, e.env0, foo], e.FUN)
+    rec = (REC, fun2[1])                                        # cast(result, Expr::Rec): same node, other tag
+    rec_env = s.intern_compact([add, rec, e.env0], e.ENV)
+
+    def head(c):
+        env = s.intern_compact([counter, e.num(c), rec_env], e.ENV)
+        return s.hide(0, s.intern_tuple4([e.lst([x]), body, env, foo], e.FUN))
+
+    c0, c1, c2 = head(0), head(9), head(21)
+    assert (c0, c1, c2) == (GOLDEN["G18"], GOLDEN["G19"], GOLDEN["G20"])
+    expr = e.lst([e.lst([e.sym("lurk", "open"), e.num(c0)]), e.num(9)])
+    out = e.cons(e.num(9), s.intern_atom(COMM, c1))
+    assert s.hide(0, e.claim(expr, e.env0, out, e.env0)) == GOLDEN["G21"]
