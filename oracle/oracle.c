@@ -16,7 +16,7 @@
  *   - Pedersen commit (MSM)    Arecibo vartime_multiscalar_mul; call sites src/proof/nova.rs:287,292
  *   - fold helpers             Arecibo NIFS::prove / commit_T / fold
  *   - NTT                      no call site in the reference: parity unpinned
- * Pinning: Poseidon digests are pinned by goldens G1..G23 (tests/test_oracle_golden.py); witness aux
+ * Pinning: Poseidon digests are pinned by goldens G1..G27 (tests/test_oracle_golden.py); witness aux
  * counts and bit-decomp sizes are pinned by src/lem/multiframe.rs:495-516,991-1016; witness aux ORDER,
  * MSM outputs and NTT are "parity unpinned" (cross-checked only against oracle/spec.py, an independent
  * from-spec Python restatement).

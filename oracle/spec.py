@@ -12,7 +12,7 @@ What it restates, with the reference call sites it follows:
       - reference call sites: src/hash.rs:61-72 (constants), src/hash.rs:180-203 (hashN)
       - neptune is a git dependency (argumentcomputer/neptune, branch dev; not in tree, no
         Cargo.lock).  Published algorithm restated here; pinned by the reference's own golden
-        digests (SURVEY.md 8(c) G1..G11 plus G13..G23 from documented REPL examples and demo scripts,
+        digests (SURVEY.md 8(c) G1..G11 plus G13..G27 from documented REPL examples and demo scripts,
         tests/golden/reference_goldens.json; src/coprocessor/trie/mod.rs:932-1010,
         src/lem/store.rs:1473, src/lem/tests/eval_tests.rs:1944,1955,3868).
   * Poseidon *witness* in Neptune's optimised-round order (src/lem/circuit.rs:212-247 call site)

@@ -306,3 +306,24 @@ def test_chained_functional_commitment_demo(oracle):
     assert claim(c0, 9, 9, c1) == GOLDEN["G21"]
     assert claim(c1, 12, 21, c2) == GOLDEN["G22"]
     assert claim(c2, 14, 35, c3) == GOLDEN["G23"]
+
+
+def test_protocol_and_chain_server_goldens(oracle):
+    """G24 (demo/protocol.lurk) and G25..G27 (chain-server/README.md): `letrec` with two bindings nests -- `add` closes over
+    the environment that already binds `sum` to its Rec -- and the head after each call differs only in the counter."""
+    REC = 13
+    e = _Exprs(oracle)
+    assert e.commit(0, e.cons(e.num(13), e.num(17))) == GOLDEN["G24"]
+    U, K = (lambda n: e.sym("lurk", "user", n)), (lambda n: e.sym("lurk", n))
+    xs, acc, sum_, add, counter = U("xs"), U("acc"), U("sum"), U("add"), U("counter")
+    body1 = e.lst([K("if"), e.lst([K("eq"), xs, e.nil]), acc,
+                   e.lst([sum_, e.lst([K("cdr"), xs]), e.lst([K("+"), acc, e.lst([K("car"), xs])])])])
+    body2 = e.lst([K("let"), e.lst([e.lst([counter, e.lst([K("+"), counter, e.lst([sum_, xs, e.num(0)])])])]),
+                   e.lst([K("cons"), counter, e.lst([K("commit"), e.lst([add, counter])])])])
+    foo = (e.NIL, 0)
+    cons4 = lambda a, b, c, d: h(oracle, BN, [*a, *b, *c, *d])
+    push = lambda s, v, env: (e.ENV, h(oracle, BN, [s[1], v[0], v[1], env[1]]))
+    env1 = push(sum_, (REC, cons4(e.lst([xs, acc]), body1, e.env0, foo)), e.env0)
+    rec_env = push(add, (REC, cons4(e.lst([counter, xs]), body2, env1, foo)), env1)
+    head = lambda c: e.commit(0, (e.FUN, cons4(e.lst([xs]), body2, push(counter, e.num(c), rec_env), foo)))
+    assert (head(0), head(7), head(37)) == (GOLDEN["G25"], GOLDEN["G26"], GOLDEN["G27"])
