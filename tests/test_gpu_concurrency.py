@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from test_gpu_dag_fold import dev, mont, unmont
-from util import ints, pack, random_elements
+from util import ints, random_elements
 
 pytestmark = pytest.mark.gpu
 
