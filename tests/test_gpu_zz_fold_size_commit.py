@@ -1,0 +1,30 @@
+"""The commitment of the fold step at bench.py's exact size, on the GPU (kept in its own file, sorted last: it was added
+after the round's GPU budget was spent, so its first run is the round-end suite)."""
+import numpy as np
+import pytest
+
+from util import ints, pack, random_elements
+
+pytestmark = pytest.mark.gpu
+
+
+def test_msm_fixed_base_fold_size_bn254(L, oracle, spec):
+    """the commitment of the fold step exactly as bench.py runs it: 2^21-point BN254 key with the fixed-base table (window
+    c = 20, one shared set of 2^19 buckets, 32-slice bucket reduction), 911 900 witness-shaped scalars.  The table path
+    must give the same point as the plain path on the same key, be linear, and match the oracle on a prefix."""
+    curve, n_key, n = 0, 1 << 21, 911_900
+    sf = spec.CURVES[curve]["scalar"]
+    bases = L.synthetic_bases(curve, n_key)
+    plain = L.CommitmentKey(curve, bases)
+    fixed = L.CommitmentKey(curve, bases).precompute()
+    a = random_elements(sf, n, seed=41, shape="witness")
+    b = random_elements(sf, n, seed=42, shape="uniform")
+    ca, cb = fixed.commit(a), fixed.commit(b)
+    assert ca[64] == 1 and spec.on_curve(curve, tuple(ints(ca[:64])))
+    assert np.array_equal(ca, plain.commit(a)) and np.array_equal(cb, plain.commit(b))
+    ab = oracle.axpy(sf, a, b, pack([1]), nthreads=8)
+    assert np.array_equal(L.point_sum(curve, np.concatenate([ca, cb])), fixed.commit(ab))          # linearity
+    m = 1 << 14
+    assert np.array_equal(fixed.commit(a[:32 * m]), oracle.msm(curve, bases[:64 * m], a[:32 * m], nthreads=8))
+    full = random_elements(sf, n_key, seed=43, shape="uniform")                                    # every base of the key
+    assert np.array_equal(fixed.commit(full), plain.commit(full))
