@@ -138,3 +138,16 @@ def test_host_group_law_properties(L, spec, curve):
         got = L.point_sum(curve, buf)
         assert np.array_equal(got, rec(want))
     check()
+
+
+def test_plain_c_client_of_the_abi(tmp_path):
+    """include/lurk_b200.h is strict C99 and a gcc-built C program can drive the library (what a cgo / bindgen shim needs):
+    host-only entry points work, compute entry points fail loudly without a GPU (tests/csrc/c_abi_client.c)"""
+    exe = str(tmp_path / "c_abi_client")
+    libdir = os.path.join(ROOT, "lurk-beta_b200")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "csrc", "c_abi_client.c"), "-o", exe, "-L", libdir, "-llurk_b200",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "c_abi_client ok" in out.stdout
