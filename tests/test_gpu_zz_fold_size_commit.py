@@ -28,3 +28,17 @@ def test_msm_fixed_base_fold_size_bn254(L, oracle, spec):
     assert np.array_equal(fixed.commit(a[:32 * m]), oracle.msm(curve, bases[:64 * m], a[:32 * m], nthreads=8))
     full = random_elements(sf, n_key, seed=43, shape="uniform")                                    # every base of the key
     assert np.array_equal(fixed.commit(full), plain.commit(full))
+
+
+def test_plain_c_client_on_the_gpu(tmp_path):
+    """the gcc-built C client (tests/csrc/c_abi_client.c) run on the GPU box: golden G1 through a process that contains no
+    Python, torch or C++ of ours -- only the C ABI"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe, libdir = str(tmp_path / "c_abi_client"), os.path.join(root, "lurk-beta_b200")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "csrc", "c_abi_client.c"),
+                           "-o", exe, "-L", libdir, "-llurk_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "c_abi_client ok" in out.stdout
