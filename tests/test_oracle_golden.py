@@ -327,3 +327,32 @@ def test_protocol_and_chain_server_goldens(oracle):
     rec_env = push(add, (REC, cons4(e.lst([counter, xs]), body2, env1, foo)), env1)
     head = lambda c: e.commit(0, (e.FUN, cons4(e.lst([xs]), body2, push(counter, e.num(c), rec_env), foo)))
     assert (head(0), head(7), head(37)) == (GOLDEN["G25"], GOLDEN["G26"], GOLDEN["G27"])
+
+
+# (1, 2) + (1, 2) on alt_bn128, the first addition vector of the Ethereum bn256Add precompile tests (EIP-196): an
+# independent known answer for the BN254 G1 group law (the reference holds no golden commitment)
+BN254_2G = (0x030644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd3,
+            0x15ed738c0e0a7c92e7845f96b2ae9c0a68a6a449e3538fc7ff3ebf7a5a18a2c4)
+
+
+def test_bn254_g1_doubling_known_answer(oracle, spec):
+    p = spec.FIELD_MODULUS[spec.CURVES[0]["base"]]
+    g = spec.CURVES[0]["gen"]
+    assert g == (1, 2) and spec.ec_mul(2, g, p) == BN254_2G and spec.ec_add(g, g, p) == BN254_2G
+    bases = oracle.gen_bases(0, 2)                               # [1]G, [2]G
+    assert tuple(ints(bases[64:128])) == BN254_2G
+    assert tuple(ints(oracle.msm(0, bases[:64], pack([2]), naive=True))[:2]) == BN254_2G
+    assert tuple(ints(oracle.msm(0, bases, pack([0, 1])))[:2]) == BN254_2G
+
+
+def test_curve_generators_are_the_published_ones(spec):
+    """the synthetic commitment keys are multiples of the standard generators: BN254 G1 (1, 2); Grumpkin (1, sqrt(-16)) with the
+    y published for the Aztec / halo2curves `grumpkin::G1::generator()`; Pallas and Vesta (-1, 2) (pasta_curves)"""
+    assert spec.CURVES[0]["gen"] == (1, 2) and spec.CURVES[0]["b"] == 3
+    assert spec.CURVES[1]["gen"] == (1, 17631683881184975370165255887551781615748388533673675138860)
+    assert spec.CURVES[1]["b"] == spec.FIELD_MODULUS[spec.CURVES[1]["base"]] - 17
+    for c in (2, 3):
+        p = spec.FIELD_MODULUS[spec.CURVES[c]["base"]]
+        assert spec.CURVES[c]["gen"] == (p - 1, 2) and spec.CURVES[c]["b"] == 5
+    for c in range(4):
+        assert spec.on_curve(c, spec.CURVES[c]["gen"])
