@@ -355,7 +355,9 @@ def on_curve(curve_id, P):
 
 # ---------------------------------------------------------------- NTT
 TWO_ADICITY = {0: 28, 1: 1, 2: 32, 3: 32}
-MULT_GEN = {0: 5, 1: 3, 2: 5, 3: 5}   # multiplicative generators used by halo2curves / pasta_curves
+# multiplicative generators of the reference's field types (ff::PrimeField::MULTIPLICATIVE_GENERATOR): halo2curves bn256::Fr 7,
+# bn256::Fq 3, pasta_curves Fp / Fq 5 -- so that 2^s-th roots equal their ROOT_OF_UNITY (checked in tests/test_oracle_golden.py)
+MULT_GEN = {0: 7, 1: 3, 2: 5, 3: 5}
 
 
 def root_of_unity(field_id, log_n):

@@ -57,3 +57,22 @@ extern "C" int fe_test_dot(int field, int k, const uint8_t *a, const uint8_t *b,
     }
     return -3;
 }
+
+// the 2^s-th root of unity the NTT kernels start from (Params::ROOT), canonical
+template <class F>
+static int run_root(uint8_t *out) {
+    F w;
+    for (int i = 0; i < 8; i++) w.v[i] = F::Params::ROOT(i);
+    w = w.to_canonical();
+    memcpy(out, w.v, 32);
+    return F::Params::TWO_ADICITY;
+}
+extern "C" int fe_test_root(int field, uint8_t *out) {
+    switch (field) {
+        case 0: return run_root<Fe<Bn254Fr>>(out);
+        case 1: return run_root<Fe<Bn254Fq>>(out);
+        case 2: return run_root<Fe<PallasFq>>(out);
+        case 3: return run_root<Fe<PallasFp>>(out);
+    }
+    return -3;
+}

@@ -151,3 +151,25 @@ def test_plain_c_client_of_the_abi(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "c_abi_client ok" in out.stdout
+
+
+# ff::PrimeField::ROOT_OF_UNITY of the reference's field types, as published in halo2curves (bn256::Fr, GENERATOR 7;
+# bn256::Fq: -1) and pasta_curves (Fq = pallas::Scalar, Fp = pallas::Base; GENERATOR 5)
+PUBLISHED_ROOT_OF_UNITY = {
+    0: 0x03ddb9f5166d18b798865ea93dd31f743215cf6dd39329c8d34f1ed960c37c9c,
+    2: 0x2de6a9b8746d3f589e5c4dfd492ae26e9bb97ea3c106f049a70e2c1102b6d05f,
+    3: 0x2bce74deac30ebda362120830561f81aea322bf2b7bb7584bdad6fabd87ea32f,
+}
+
+
+@pytest.mark.parametrize("field", [0, 1, 2, 3])
+def test_ntt_root_of_unity_is_the_field_types_own(fieldlib, spec, field):
+    """the NTT kernels (csrc/ntt.cu: omega = ROOT^(2^(s - log n))), the oracle and the reference's field types agree on the
+    2^s-th root of unity: a transform computed with another primitive root is a permutation of this one"""
+    p = spec.FIELD_MODULUS[field]
+    out = ctypes.create_string_buffer(32)
+    s = fieldlib.fe_test_root(field, out)
+    root = int.from_bytes(out.raw, "little")
+    assert s == spec.TWO_ADICITY[field] and root == spec.root_of_unity(field, s)
+    assert pow(root, 1 << s, p) == 1 and pow(root, 1 << (s - 1), p) == p - 1
+    assert root == PUBLISHED_ROOT_OF_UNITY.get(field, p - 1)
