@@ -183,6 +183,107 @@ int lurk_cross_term_dev(int field_id, const void *d_az1, const void *d_bz1, cons
 int lurk_convert_dev(int field_id, const void *d_in, size_t n, int to_fmt, void *d_out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * S5/S6  Fold context: the GPU half of `Proof::prove_recursively` (src/proof/nova.rs:260-339, supernova.rs:207-291) for
+ *     ONE running instance, i.e. what RecursiveSNARK::new / prove_step (nova.rs:286-293) do with the primary circuit's
+ *     witness inside Arecibo's NIFS::prove, on device-resident state:
+ *         comm_W2 = commit(W2); T = cross term; comm_T = commit(T); r = RO(..., comm_W2, ..., comm_T);
+ *         (W, u, X) += r (W2, 1, X2); E += r T; comm_W += r comm_W2; comm_E += r comm_T.
+ *     The reference overlaps a witness thread with the fold thread over a bounded channel (nova.rs:297-326); here stage A
+ *     (inputs, slot witnesses, commit(W2), A z2 .. C z2) of up to `depth - 1` later steps runs on its own CUDA streams while
+ *     stage B -- the sequential chain -- runs without any host round trip: the commitments are finished, exchanged between
+ *     GPUs (peer memory over NVLink), normalised, hashed into the challenge and consumed by the fold on the device.
+ *     SuperNova / NIVC: one context per circuit index (src/lem/multiframe.rs:941), all sharing one commitment key.
+ *     z = (W, u, X).  Matrices are CSR over z's columns.  All calls of one context must come from one thread at a time.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct lurk_fold_ctx lurk_fold_ctx;
+typedef struct lurk_fold_config {
+    int curve_id;            /* commitments on this curve; the witness field is its scalar field */
+    int depth;               /* fresh-instance buffers, 1..4: stage A may run depth - 1 steps ahead of the fold */
+    uint64_t n_w;            /* |W| of this rank's share */
+    uint64_t n_x;            /* |X| (2 for Nova step circuits) */
+    uint64_t n_rows;         /* constraints of this rank's share */
+    const uint64_t *row_ptr[3]; /* A, B, C: rows + 1 offsets                                    (host) */
+    const uint32_t *col[3];     /* column of every non-zero, < n_w + 1 + n_x                     (host) */
+    const uint8_t *val[3];      /* coefficient of every non-zero, 32 bytes each, in `fmt`        (host) */
+    int fmt;
+    int world, rank;         /* > 1: the key is sharded; the partial commitments are exchanged every step */
+    int latency_sms;         /* 0 = off; otherwise SMs reserved for the latency-shaped kernels of the chain (green
+                                contexts; multiple of 8, e.g. 16): bucket accumulation and stage A get the rest */
+} lurk_fold_config;
+/* ck_w / ck_t: this rank's bases for W (>= n_w points) and for T / E (>= n_rows points); the same context when the key is
+ * not sharded.  Fixed-base tables are built if absent.  The contexts must outlive the fold context. */
+int lurk_fold_ctx_create(const lurk_fold_config *cfg, lurk_msm_ctx *ck_w, lurk_msm_ctx *ck_t, lurk_fold_ctx **out);
+void lurk_fold_ctx_destroy(lurk_fold_ctx *ctx);
+/* One batch per slot type of the step circuit (generate_slots_witnesses, src/lem/multiframe.rs:520-592): arity 3/4/6/8 =
+ * Poseidon slots, 0 = bit-decomposition slots.  offsets[k] = element offset of block k inside W (the reference's layout:
+ * every frame's aux = [its slot blocks | LEM body aux], multiframe.rs:635-712).  Returns the batch index (>= 0). */
+int lurk_fold_ctx_add_slot_batch(lurk_fold_ctx *ctx, int arity, size_t count, const uint64_t *offsets);
+/* The parts of W2 the host produces (LEM body aux, the augmented-circuit part): up to 4 strided spans of W; the host
+ * buffer LURK_FOLD_BUF_GLUE holds them densely, span after span, row after row. */
+typedef struct lurk_fold_span { uint64_t first, row_elems, stride, rows; } lurk_fold_span;
+int lurk_fold_ctx_set_spans(lurk_fold_ctx *ctx, int n_spans, const lurk_fold_span *spans);
+/* Random oracle = Arecibo's PoseidonRO (neptune sponge, arity 24, [Absorb(n), Squeeze(1)], low `challenge_bits` bits).
+ * kinds[i] says what is absorbed at position i.  Default (NIFS::prove): CONST pp_digest, W_X, W_Y, W_INF, CONST X2[0],
+ * CONST X2[1], T_X, T_Y, T_INF with 128 bits.  CONST values come from the host buffer LURK_FOLD_BUF_RO of the step. */
+#define LURK_FOLD_RO_CONST 0
+#define LURK_FOLD_RO_W_X 1
+#define LURK_FOLD_RO_W_Y 2
+#define LURK_FOLD_RO_W_INF 3
+#define LURK_FOLD_RO_T_X 4
+#define LURK_FOLD_RO_T_Y 5
+#define LURK_FOLD_RO_T_INF 6
+int lurk_fold_ctx_set_ro(lurk_fold_ctx *ctx, int n_absorb, const int *kinds, int challenge_bits);
+/* Pinned host buffers the caller (the CPU witness generator) fills before stage A of buffer b: `which` >= 0 = preimages
+ * of that slot batch (count * arity elements; bit decomposition: count values), or one of the names below. */
+#define LURK_FOLD_BUF_GLUE (-1) /* the spans, densely                       (witness field)            */
+#define LURK_FOLD_BUF_X2 (-2)   /* public IO of the fresh instance, n_x      (witness field)            */
+#define LURK_FOLD_BUF_RO (-3)   /* 24 elements: position i = CONST value of RO slot i (commitment curve's base field) */
+#define LURK_FOLD_BUF_W2 (-4)   /* device only: z2 of buffer b = (W2, 1, X2), Montgomery               */
+#define LURK_FOLD_BUF_T (-5)    /* device only: cross term of the last step                             */
+#define LURK_FOLD_BUF_Z1 (-6)   /* device only: running z = (W, u, X)                                   */
+#define LURK_FOLD_BUF_E1 (-7)   /* device only: running E                                               */
+int lurk_fold_ctx_host_buffer(lurk_fold_ctx *ctx, int b, int which, void **ptr, size_t *bytes);
+int lurk_fold_ctx_device_buffer(lurk_fold_ctx *ctx, int b, int which, void **d_ptr, size_t *bytes);
+/* Sharded key, one process per GPU: every rank publishes a 64-byte handle of its exchange buffer (any transport: e.g. a
+ * torch.distributed all_gather of the bytes) and receives all `world` handles, ordered by rank. */
+int lurk_fold_ctx_exchange_handle(lurk_fold_ctx *ctx, uint8_t handle[64]);
+int lurk_fold_ctx_set_peers(lurk_fold_ctx *ctx, const uint8_t *handles /* world * 64 bytes */);
+/* Running instance (checkpoint / resume: prove_recursively's `init: Option<RecursiveSNARK>`, src/proof/mod.rs:107-115).
+ * comm_* are 96-byte points x | y | z as everywhere in this header; any output pointer of _get_ may be NULL. */
+int lurk_fold_ctx_set_running(lurk_fold_ctx *ctx, const uint8_t *W, const uint8_t *E, const uint8_t u[32], const uint8_t *X,
+                              const uint8_t comm_W[96], const uint8_t comm_E[96], int fmt);
+int lurk_fold_ctx_get_running(lurk_fold_ctx *ctx, uint8_t *W, uint8_t *E, uint8_t u[32], uint8_t *X, uint8_t comm_W[96],
+                              uint8_t comm_E[96], int fmt);
+/* Stage A of the step whose inputs are in the host buffers of b (fmt = their format).  LURK_FOLD_INPUTS_RESIDENT: skip
+ * the host-to-device copies and use what the device buffers hold (Montgomery). Asynchronous. */
+#define LURK_FOLD_INPUTS_RESIDENT 1
+int lurk_fold_ctx_stage_a(lurk_fold_ctx *ctx, int b, int flags, int fmt);
+/* RecursiveSNARK::new: the running instance becomes the fresh instance of buffer b (u = 1, E = 0, comm_E = identity). */
+int lurk_fold_ctx_init_running(lurk_fold_ctx *ctx, int b);
+/* Stage B: enqueues the whole fold of the fresh instance in buffer b onto the running instance.  Asynchronous; call
+ * stage_a for later steps and stage_b_launch for the next step without waiting. */
+int lurk_fold_ctx_stage_b_launch(lurk_fold_ctx *ctx, int b);
+typedef struct lurk_fold_result {
+    uint8_t comm_W[96];         /* commitment to the fresh witness (whole key) */
+    uint8_t comm_T[96];         /* commitment to the cross term; identity after init_running */
+    uint8_t r[32];              /* the challenge as an element of the witness field */
+    uint8_t running_comm_W[96]; /* after this step's fold */
+    uint8_t running_comm_E[96];
+    uint8_t ro_hash[32];        /* the squeezed sponge element before truncation (commitment curve's base field) */
+    int status;
+    uint64_t seq;               /* exchange epoch = number of commitments finished by this context */
+} lurk_fold_result;
+/* waits for the step enqueued on buffer b (init_running or stage_b_launch) and returns its record */
+int lurk_fold_ctx_collect(lurk_fold_ctx *ctx, int b, lurk_fold_result *out, int fmt);
+/* Verifier-side sanity of the running instance, computed on the device: rows with (A z) o (B z) != u (C z) + E, and
+ * whether commit(W) / commit(E) recomputed from the vectors equal the folded commitments.  Synchronous. */
+int lurk_fold_ctx_check_running(lurk_fold_ctx *ctx, uint64_t *bad_rows, int *comm_W_ok, int *comm_E_ok);
+/* kernels enqueued by the last stage A / stage B, device time of the bucket-accumulation kernels of the last commit(W2) of
+ * buffer 0 and of the last commit(T) (CUDA events on the launching streams).  Synchronises the context. */
+int lurk_fold_ctx_stats(lurk_fold_ctx *ctx, unsigned *launches_a, unsigned *launches_b, float *accumulate_w_ms, float *accumulate_t_ms);
+int lurk_fold_ctx_sync(lurk_fold_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------------------
  * K6  Number-theoretic transform (north_star; no call site in the reference -- SURVEY.md D4).
  *     In-place length-2^log_n DFT over the field's 2-adic subgroup, natural order in and out, Montgomery form.
  *     Roots: omega = g^((p-1)/2^s) with g the multiplicative generator of halo2curves / pasta_curves.

@@ -9,13 +9,14 @@ from . import _capi
 from ._capi import (CURVE_BN254_G1, CURVE_GRUMPKIN, CURVE_PALLAS, CURVE_VESTA, FIELD_BN254_FQ, FIELD_BN254_FR,
                     FIELD_PALLAS_FP, FIELD_PALLAS_FQ, FMT_CANONICAL, FMT_MONTGOMERY, LurkError)
 from .commit import CommitmentKey, ShardedCommitmentKey, point_sum, shard_bounds, synthetic_bases
+from .fold import NovaFoldContext, SuperNovaFoldContext
 from .hash import HashConstants, PoseidonCache
 from .slots import SlotType, compute_witness_size, generate_slots_witnesses, slot_witness_batch_bytes
 from .store import StoreCore
 from .trie import StandardTrie, Trie
 
 __all__ = [
-    "CommitmentKey", "ShardedCommitmentKey", "point_sum", "shard_bounds", "synthetic_bases", "HashConstants", "PoseidonCache", "SlotType",
+    "CommitmentKey", "ShardedCommitmentKey", "NovaFoldContext", "SuperNovaFoldContext", "point_sum", "shard_bounds", "synthetic_bases", "HashConstants", "PoseidonCache", "SlotType",
     "compute_witness_size", "generate_slots_witnesses", "slot_witness_batch_bytes", "StoreCore", "StandardTrie", "Trie", "LurkError",
     "FIELD_BN254_FR", "FIELD_BN254_FQ", "FIELD_PALLAS_FQ", "FIELD_PALLAS_FP", "CURVE_BN254_G1", "CURVE_GRUMPKIN",
     "CURVE_PALLAS", "CURVE_VESTA", "FMT_CANONICAL", "FMT_MONTGOMERY",

@@ -22,6 +22,25 @@ class DagNode(C.Structure):
     _fields_ = [("kind", C.c_uint8), ("reserved", C.c_uint8), ("tag", C.c_uint16 * 4), ("child", C.c_uint32 * 4)]
 
 
+class FoldConfig(C.Structure):
+    _fields_ = [("curve_id", C.c_int), ("depth", C.c_int), ("n_w", C.c_uint64), ("n_x", C.c_uint64), ("n_rows", C.c_uint64),
+                ("row_ptr", C.c_void_p * 3), ("col", C.c_void_p * 3), ("val", C.c_void_p * 3), ("fmt", C.c_int),
+                ("world", C.c_int), ("rank", C.c_int), ("latency_sms", C.c_int)]
+
+
+class FoldSpan(C.Structure):
+    _fields_ = [("first", C.c_uint64), ("row_elems", C.c_uint64), ("stride", C.c_uint64), ("rows", C.c_uint64)]
+
+
+class FoldResult(C.Structure):
+    _fields_ = [("comm_W", C.c_uint8 * 96), ("comm_T", C.c_uint8 * 96), ("r", C.c_uint8 * 32), ("running_comm_W", C.c_uint8 * 96),
+                ("running_comm_E", C.c_uint8 * 96), ("ro_hash", C.c_uint8 * 32), ("status", C.c_int), ("seq", C.c_uint64)]
+
+
+FOLD_BUF_GLUE, FOLD_BUF_X2, FOLD_BUF_RO, FOLD_BUF_W2, FOLD_BUF_T, FOLD_BUF_Z1, FOLD_BUF_E1 = -1, -2, -3, -4, -5, -6, -7
+FOLD_INPUTS_RESIDENT = 1
+FOLD_RO_CONST, FOLD_RO_W_X, FOLD_RO_W_Y, FOLD_RO_W_INF, FOLD_RO_T_X, FOLD_RO_T_Y, FOLD_RO_T_INF = range(7)
+
 _vp, _sz, _i = C.c_void_p, C.c_size_t, C.c_int
 # every symbol declared in include/lurk_b200.h: name -> (restype, argtypes)
 PROTOTYPES = {
@@ -61,6 +80,24 @@ PROTOTYPES = {
     "lurk_cross_term_dev": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "lurk_convert_dev": (_i, [_i, _vp, _sz, _i, _vp, _vp]),
     "lurk_ntt_dev": (_i, [_i, _vp, _i, _i, _vp]),
+    "lurk_fold_ctx_create": (_i, [C.POINTER(FoldConfig), _vp, _vp, C.POINTER(_vp)]),
+    "lurk_fold_ctx_destroy": (None, [_vp]),
+    "lurk_fold_ctx_add_slot_batch": (_i, [_vp, _i, _sz, _vp]),
+    "lurk_fold_ctx_set_spans": (_i, [_vp, _i, C.POINTER(FoldSpan)]),
+    "lurk_fold_ctx_set_ro": (_i, [_vp, _i, C.POINTER(_i), _i]),
+    "lurk_fold_ctx_host_buffer": (_i, [_vp, _i, _i, C.POINTER(_vp), C.POINTER(_sz)]),
+    "lurk_fold_ctx_device_buffer": (_i, [_vp, _i, _i, C.POINTER(_vp), C.POINTER(_sz)]),
+    "lurk_fold_ctx_exchange_handle": (_i, [_vp, _vp]),
+    "lurk_fold_ctx_set_peers": (_i, [_vp, _vp]),
+    "lurk_fold_ctx_set_running": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "lurk_fold_ctx_get_running": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "lurk_fold_ctx_stage_a": (_i, [_vp, _i, _i, _i]),
+    "lurk_fold_ctx_init_running": (_i, [_vp, _i]),
+    "lurk_fold_ctx_stage_b_launch": (_i, [_vp, _i]),
+    "lurk_fold_ctx_collect": (_i, [_vp, _i, C.POINTER(FoldResult), _i]),
+    "lurk_fold_ctx_check_running": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(_i), C.POINTER(_i)]),
+    "lurk_fold_ctx_stats": (_i, [_vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "lurk_fold_ctx_sync": (_i, [_vp]),
 }
 
 _lib = None

@@ -40,9 +40,10 @@ struct DevBuf {
     ~DevBuf() { if (p) cudaFree(p); }
     int alloc(size_t n) {
         if (p) { cudaFree(p); p = nullptr; }
-        bytes = n;
+        bytes = 0;                       // stays 0 when cudaMalloc fails: `bytes >= want` must never hide a null buffer
         if (n == 0) return LURK_OK;
         LURK_CUDA_TRY(cudaMalloc(&p, n));
+        bytes = n;
         return LURK_OK;
     }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }

@@ -258,6 +258,46 @@ struct alignas(16) Fe {
         }
         return acc;
     }
+    // Variable-time inversion by the binary extended Euclidean algorithm (shifts, adds and compares only: ~6x fewer
+    // dependent multiplier instructions than Fermat for a single thread, which is what the one-thread affine
+    // normalisation on the fold's critical chain needs).  Montgomery form in and out; 0 -> 0.
+    // Invariants: x1 * a == u, x2 * a == v (mod p) with a the raw input; gcd(a, p) = 1 so the loop ends with u or v = 1.
+    LURK_HD Fe inv_vartime() const {
+        if (is_zero()) return zero();
+        uint32_t u[8], w[8];
+        Fe x1 = zero(), x2 = zero();
+        x1.v[0] = 1;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { u[i] = v[i]; w[i] = P::MOD(i); }
+        auto is_one = [](const uint32_t *a) { uint32_t o = a[0] ^ 1u; for (int i = 1; i < 8; i++) o |= a[i]; return o == 0; };
+        auto shr1 = [](uint32_t *a) { for (int i = 0; i < 7; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31); a[7] >>= 1; };
+        auto halve = [&](Fe &x) {                 // x / 2 mod p on a raw value < p (p < 2^255: x + p cannot overflow)
+            if (x.v[0] & 1u) {
+                x.v[0] = cc::add_cc(x.v[0], P::MOD(0));
+                for (int i = 1; i < 7; i++) x.v[i] = cc::addc_cc(x.v[i], P::MOD(i));
+                x.v[7] = cc::addc(x.v[7], P::MOD(7));
+            }
+            shr1(x.v);
+        };
+        auto sub_raw = [](uint32_t *a, const uint32_t *b) {   // a -= b, returns the borrow mask
+            a[0] = cc::sub_cc(a[0], b[0]);
+            for (int i = 1; i < 8; i++) a[i] = cc::subc_cc(a[i], b[i]);
+            return cc::subc(0, 0);
+        };
+        auto geq = [](const uint32_t *a, const uint32_t *b) {
+            for (int i = 7; i >= 0; i--) { if (a[i] > b[i]) return true; if (a[i] < b[i]) return false; }
+            return true;
+        };
+        while (!is_one(u) && !is_one(w)) {
+            while (!(u[0] & 1u)) { shr1(u); halve(x1); }
+            while (!(w[0] & 1u)) { shr1(w); halve(x2); }
+            if (geq(u, w)) { sub_raw(u, w); x1 = x1 - x2; }
+            else { sub_raw(w, u); x2 = x2 - x1; }
+        }
+        // raw inverse X = (aR)^-1; the Montgomery form of the inverse is a^-1 R = X R^2 = mont(X, R^3)
+        const Fe r3 = rr() * rr();
+        return (is_one(u) ? x1 : x2) * r3;
+    }
     // Fermat inversion; 0 -> 0
     LURK_HD Fe inv() const {
         uint32_t e[8];

@@ -47,13 +47,17 @@ template <class F>
 int check_reduced_dev(const void *d_in, size_t n, cudaStream_t s, int *bad_host) {
     *bad_host = 0;
     if (n == 0) return LURK_OK;
+    // stream-ordered scratch: cudaMalloc / cudaFree would synchronise the whole device inside every host-buffer call
     int *d_bad = nullptr;
-    LURK_CUDA_TRY(cudaMalloc(&d_bad, sizeof(int)));
-    cudaMemsetAsync(d_bad, 0, sizeof(int), s);
-    check_reduced_kernel<F><<<stream_grid(n, 256, 8), 256, 0, s>>>((const F *)d_in, n, d_bad);
-    cudaError_t e = cudaMemcpyAsync(bad_host, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s);
+    LURK_CUDA_TRY(cudaMallocAsync(&d_bad, sizeof(int), s));
+    cudaError_t e = cudaMemsetAsync(d_bad, 0, sizeof(int), s);
+    if (e == cudaSuccess) {
+        check_reduced_kernel<F><<<stream_grid(n, 256, 8), 256, 0, s>>>((const F *)d_in, n, d_bad);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bad_host, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaFreeAsync(d_bad, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFree(d_bad);
     LURK_CUDA_TRY(e);
     return LURK_OK;
 }

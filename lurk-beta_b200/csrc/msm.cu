@@ -59,6 +59,7 @@ void lurk_msm_ctx_destroy(lurk_msm_ctx *ctx) {
     if (!ctx) return;
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     if (ctx->done) cudaEventDestroy(ctx->done);
+    if (ctx->ev_fork) { cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
     if (ctx->owns_bases && ctx->d_bases) cudaFree(ctx->d_bases);
     if (ctx->owns_table && ctx->d_table) cudaFree(ctx->d_table);
     delete ctx;
@@ -77,7 +78,7 @@ int lurk_msm_ctx_launch_dev(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, 
     if (fmt != LURK_FMT_CANONICAL && fmt != LURK_FMT_MONTGOMERY) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
     if (n > ctx->n) { set_error("%zu scalars for a commitment key of %zu bases", n, ctx->n); return LURK_ERR_ARG; }
     std::lock_guard<std::mutex> g(ctx->mu);
-    return dispatch_curve(ctx->curve_id, [&](auto c) { return msm_launch<decltype(c)>(ctx, d_scalars, n, fmt, (cudaStream_t)stream); });
+    return dispatch_curve(ctx->curve_id, [&](auto c) { return msm_launch<decltype(c)>(ctx, d_scalars, n, fmt, (cudaStream_t)stream, true); });
 }
 int lurk_msm_ctx_finish(lurk_msm_ctx *ctx, uint8_t out_xyz[96]) {
     if (!ctx || !out_xyz) { set_error("null argument"); return LURK_ERR_ARG; }
@@ -120,6 +121,8 @@ int lurk_msm_ctx_run(lurk_msm_ctx *ctx, const uint8_t *scalars, size_t n, int fm
     // upload through two pinned staging buffers: the memcpy out of the caller's pageable memory overlaps the DMA
     MsmScratch &S = ctx->scratch;
     const size_t STAGE = (size_t)8 << 20;
+    if (!S.stage_stream) LURK_CUDA_TRY(cudaStreamCreateWithFlags(&S.stage_stream, cudaStreamNonBlocking));
+    cudaStream_t hs = S.stage_stream;      // not the legacy default stream: that one serialises against every other stream
     if (!S.h_stage[0]) {
         for (int k = 0; k < 2; k++) {
             LURK_CUDA_TRY(cudaMallocHost(&S.h_stage[k], STAGE));
@@ -132,16 +135,16 @@ int lurk_msm_ctx_run(lurk_msm_ctx *ctx, const uint8_t *scalars, size_t n, int fm
         const size_t len = std::min(STAGE, total - off);
         LURK_CUDA_TRY(cudaEventSynchronize(S.stage_done[k]));      // the previous DMA out of this buffer is complete
         memcpy(S.h_stage[k], scalars + off, len);
-        LURK_CUDA_TRY(cudaMemcpyAsync((uint8_t *)S.scalars.p + off, S.h_stage[k], len, cudaMemcpyHostToDevice, nullptr));
-        LURK_CUDA_TRY(cudaEventRecord(S.stage_done[k], nullptr));
+        LURK_CUDA_TRY(cudaMemcpyAsync((uint8_t *)S.scalars.p + off, S.h_stage[k], len, cudaMemcpyHostToDevice, hs));
+        LURK_CUDA_TRY(cudaEventRecord(S.stage_done[k], hs));
     }
     int bad = 0;
     LURK_TRY(dispatch_curve(ctx->curve_id, [&](auto c) {
         using Fs = typename decltype(c)::Scalar;
-        return check_reduced_dev<Fs>(ctx->scratch.scalars.p, n, 0, &bad);
+        return check_reduced_dev<Fs>(ctx->scratch.scalars.p, n, hs, &bad);
     }));
     if (bad) { set_error("%d scalar(s) are not reduced below the group order", bad); return LURK_ERR_RANGE; }
-    return dispatch_curve(ctx->curve_id, [&](auto c) { return msm_run<decltype(c)>(ctx, ctx->scratch.scalars.p, n, fmt, out_xyz, nullptr); });
+    return dispatch_curve(ctx->curve_id, [&](auto c) { return msm_run<decltype(c)>(ctx, ctx->scratch.scalars.p, n, fmt, out_xyz, hs); });
 }
 
 int lurk_msm(int curve_id, const uint8_t *bases_affine, const uint8_t *scalars, size_t n, int fmt, uint8_t out_xyz[96]) {

@@ -424,6 +424,31 @@ __global__ void __launch_bounds__(128) msm_slice_sum_kernel(const XYZZ<Fb> *__re
     if (lane == 0) store_xyzz(out + gw, pt);
 }
 
+// level 3 (fixed-base mode: one bucket set): R = T + K * sum_k 2^k S_k on the device, one warp.  Lane 0 holds T, lane q >= 1
+// holds S_(q-1) and doubles it log2(K) + q - 1 times; a butterfly of 5 additions sums the lanes.  Longest chain:
+// log2(K) + nq - 2 doublings + 5 additions (21 + 5 for a 2^21-point key) instead of the 36 sequential operations of a
+// Horner walk -- this kernel sits on the fold's critical chain.  The result stays on the device (XYZZ, 128 bytes) for the
+// fold context's challenge kernel; lurk_msm_ctx_finish reads it back and normalises it on the host.
+template <class Fb>
+__global__ void __launch_bounds__(32) msm_horner_kernel(const XYZZ<Fb> *__restrict__ wins, uint32_t nq, uint32_t K, XYZZ<Fb> *__restrict__ out) {
+    const uint32_t lane = threadIdx.x;
+    XYZZ<Fb> pt = XYZZ<Fb>::identity();
+    if (lane < nq) pt = load_xyzz(wins + lane);
+    uint32_t logk = 0;
+    while ((1u << logk) < K) logk++;
+    const uint32_t mine = (lane >= 1 && lane < nq) ? logk + lane - 1 : 0;
+    const uint32_t longest = nq >= 2 ? logk + nq - 2 : 0;
+#pragma unroll 1
+    for (uint32_t d = 0; d < longest; d++)
+        if (d < mine) pt = pt.dbl();
+#pragma unroll 1
+    for (int d = 16; d > 0; d >>= 1) {
+        const XYZZ<Fb> p2 = shfl_xor_xyzz(pt, d);
+        pt.add(p2);
+    }
+    if (lane == 0) store_xyzz(out, pt);
+}
+
 // Fixed-base table: table[w * n + i] = 2^(c w) * bases[i], affine.  One thread per base walks the windows with c
 // doublings each (XYZZ), then normalises its nwin points with one inversion (Montgomery's trick on the ZZZ coordinates).
 static constexpr int MSM_MAX_TABLE_WINDOWS = 26;
@@ -484,12 +509,14 @@ __global__ void __launch_bounds__(256) msm_bases_to_mont_kernel(Fb *coords, size
 
 // ----------------------------------------------------------------------------- context
 struct MsmScratch {
-    DevBuf counts, offsets, tiles, sorted, buckets, pkey[2], ppt[2], chunks, chunk_sums, slices, wins, scalars;
+    DevBuf counts, offsets, tiles, sorted, buckets, pkey[2], ppt[2], chunks, chunk_sums, slices, wins, result, scalars;
     void *h_wins = nullptr;   // pinned
     void *h_stage[2] = {nullptr, nullptr};          // pinned staging for host-buffer scalars
     cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    cudaStream_t stage_stream = nullptr;            // private non-blocking stream of the host-buffer entry point
     ~MsmScratch() {
         if (h_wins) cudaFreeHost(h_wins);
+        if (stage_stream) cudaStreamDestroy(stage_stream);
         for (int k = 0; k < 2; k++) { if (h_stage[k]) cudaFreeHost(h_stage[k]); if (stage_done[k]) cudaEventDestroy(stage_done[k]); }
     }
 };
@@ -520,6 +547,11 @@ struct lurk_msm_ctx {
     bool pending_fixed = false;
     uint32_t pending_nq = 0, pending_K = 0;
     cudaEvent_t done = nullptr;
+    // optional SM partitioning (set by the fold context): the bucket-accumulation kernel -- the one throughput-shaped kernel
+    // of the pipeline -- is enqueued on `acc_stream` (a stream of another green context) between two events, the
+    // latency-shaped rest stays on the caller's stream
+    cudaStream_t acc_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace lurk {
@@ -544,7 +576,7 @@ inline int ctx_check_device(const lurk_msm_ctx *ctx) {
 
 // enqueue the whole pipeline on stream s, ending with the async read-back of the window sums
 template <class C>
-int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cudaStream_t s) {
+int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cudaStream_t s, bool readback) {
     using Fb = typename C::Base;
     using Fs = typename C::Scalar;
     using Pt = XYZZ<Fb>;
@@ -553,12 +585,18 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
     if (!ctx->done) LURK_CUDA_TRY(cudaEventCreateWithFlags(&ctx->done, cudaEventDisableTiming));
     ctx->pending_fmt = fmt;
     ctx->pending_nwin = 0;
-    if (n == 0) { ctx->pending = true; return LURK_OK; }
+    MsmScratch &S = ctx->scratch;
+    if (S.result.bytes < sizeof(Pt)) LURK_TRY(S.result.alloc(sizeof(Pt)));
+    if (n == 0) {
+        if (readback) ctx->pending = true;
+        else LURK_CUDA_TRY(cudaMemsetAsync(S.result.p, 0, sizeof(Pt), s));     // all-zero XYZZ = identity
+        return LURK_OK;
+    }
     const bool fixed = ctx->d_table != nullptr;
+    if (!readback && !fixed) { set_error("device-resident results need the fixed-base table (lurk_msm_ctx_precompute)"); return LURK_ERR_ARG; }
     MsmPlan P = make_plan(n, Fs::Params::NBITS, fixed ? ctx->fixed_c : 0);
     // sorted-entry offsets are 32-bit: one launch handles < 2^32 (scalar, window) pairs; larger keys are sharded
     if ((uint64_t)n * (uint64_t)P.nwin >= (1ull << 32)) { set_error("%zu scalars exceed one launch (shard the commitment key)", n); return LURK_ERR_ARG; }
-    MsmScratch &S = ctx->scratch;
     const uint32_t TB = P.total_buckets;
     const uint32_t ntiles = (TB + SCAN_TILE - 1) / SCAN_TILE;
     {
@@ -601,14 +639,24 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
     msm_scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_sums, ntiles, tile_offsets);
     msm_scan_apply_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_offsets, ntiles, offsets);
     msm_scatter_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, key_stride, base_stride, offsets, cursor, sorted);
-    if (ctx->profile) cudaEventRecord(ctx->ev0, s);
+    cudaStream_t sa = s;
+    if (ctx->acc_stream && ctx->acc_stream != s) {
+        sa = ctx->acc_stream;
+        LURK_CUDA_TRY(cudaEventRecord(ctx->ev_fork, s));
+        LURK_CUDA_TRY(cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
+    }
+    if (ctx->profile) LURK_CUDA_TRY(cudaEventRecord(ctx->ev0, sa));
     if (fixed)
-        msm_accumulate_kernel<Fb, 5><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
-                                                                       S.ppt[0].as<Pt>(), P.seg, P.t1);
+        msm_accumulate_kernel<Fb, 5><<<(P.t1 + 127) / 128, 128, 0, sa>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
+                                                                        S.ppt[0].as<Pt>(), P.seg, P.t1);
     else
-        msm_accumulate_kernel<Fb, 4><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
-                                                                       S.ppt[0].as<Pt>(), P.seg, P.t1);
-    if (ctx->profile) cudaEventRecord(ctx->ev1, s);
+        msm_accumulate_kernel<Fb, 4><<<(P.t1 + 127) / 128, 128, 0, sa>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
+                                                                        S.ppt[0].as<Pt>(), P.seg, P.t1);
+    if (ctx->profile) LURK_CUDA_TRY(cudaEventRecord(ctx->ev1, sa));
+    if (sa != s) {
+        LURK_CUDA_TRY(cudaEventRecord(ctx->ev_join, sa));
+        LURK_CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    }
     launches += 6;
     // shrinking passes over the partial list: one throughput-shaped pass (8 entries per thread), then warp-cooperative
     // passes (32x per pass, 5 dependent additions each) until a single warp finishes
@@ -643,9 +691,15 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
         msm_slice_sum_kernel<Fb><<<(nres * 32 + 127) / 128, 128, 0, s>>>(S.slices.as<Pt>(), P.SL, nres, S.wins.as<Pt>());
         launches++;
     }
+    if (fixed) {   // one bucket set: finish the weighted sum on the device (result stays resident for chained consumers)
+        msm_horner_kernel<Fb><<<1, 32, 0, s>>>(S.wins.as<Pt>(), P.nq, P.K, S.result.as<Pt>());
+        launches++;
+    }
     ctx->last_launches = launches;
     LURK_CUDA_TRY(cudaGetLastError());
-    LURK_CUDA_TRY(cudaMemcpyAsync(S.h_wins, S.wins.p, (size_t)nres * sizeof(Pt), cudaMemcpyDeviceToHost, s));
+    if (!readback) return LURK_OK;
+    if (fixed) LURK_CUDA_TRY(cudaMemcpyAsync(S.h_wins, S.result.p, sizeof(Pt), cudaMemcpyDeviceToHost, s));
+    else LURK_CUDA_TRY(cudaMemcpyAsync(S.h_wins, S.wins.p, (size_t)nres * sizeof(Pt), cudaMemcpyDeviceToHost, s));
     LURK_CUDA_TRY(cudaEventRecord(ctx->done, s));
     ctx->pending = true;
     ctx->pending_c = P.c;
@@ -679,7 +733,7 @@ int msm_finish(lurk_msm_ctx *ctx, uint8_t out[96]) {
     };
     Pt acc = Pt::identity();
     if (ctx->pending_fixed) {
-        acc = bucket_set(0);                       // the table already carries the 2^(c w) factors
+        acc = h[0];                                // msm_horner_kernel: the table already carries the 2^(c w) factors
     } else {
         for (int i = ctx->pending_nwin - 1; i >= 0; i--) {
             for (int d = 0; d < ctx->pending_c; d++) acc = acc.dbl();
@@ -692,7 +746,7 @@ int msm_finish(lurk_msm_ctx *ctx, uint8_t out[96]) {
 
 template <class C>
 int msm_run(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, uint8_t out[96], cudaStream_t s) {
-    LURK_TRY(msm_launch<C>(ctx, d_scalars, n, fmt, s));
+    LURK_TRY(msm_launch<C>(ctx, d_scalars, n, fmt, s, true));
     return msm_finish<C>(ctx, out);
 }
 
@@ -745,13 +799,13 @@ int msm_precompute(lurk_msm_ctx *ctx) {
 
 // everything that launches kernels, instantiated once per curve in msm_inst.cu
 #define LURK_MSM_INSTANTIATE(C)                                                                    \
-    template int msm_launch<C>(lurk_msm_ctx *, const void *, size_t, int, cudaStream_t);          \
+    template int msm_launch<C>(lurk_msm_ctx *, const void *, size_t, int, cudaStream_t, bool);    \
     template int msm_finish<C>(lurk_msm_ctx *, uint8_t *);                                         \
     template int msm_run<C>(lurk_msm_ctx *, const void *, size_t, int, uint8_t *, cudaStream_t);  \
     template int ctx_upload<C>(lurk_msm_ctx *, const uint8_t *, size_t, int);                      \
     template int msm_precompute<C>(lurk_msm_ctx *);
 #define LURK_MSM_EXTERN(C)                                                                                \
-    extern template int msm_launch<C>(lurk_msm_ctx *, const void *, size_t, int, cudaStream_t);          \
+    extern template int msm_launch<C>(lurk_msm_ctx *, const void *, size_t, int, cudaStream_t, bool);    \
     extern template int msm_finish<C>(lurk_msm_ctx *, uint8_t *);                                         \
     extern template int msm_run<C>(lurk_msm_ctx *, const void *, size_t, int, uint8_t *, cudaStream_t);  \
     extern template int ctx_upload<C>(lurk_msm_ctx *, const uint8_t *, size_t, int);                      \

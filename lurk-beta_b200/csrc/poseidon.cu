@@ -105,7 +105,10 @@ static int run_host(int arity, const uint8_t *pre, size_t n, uint8_t *out, int i
         g_pool.device = dev;
     }
     if (!g_pool.d_bad) LURK_CUDA_TRY(cudaMalloc(&g_pool.d_bad, sizeof(int)));
-    LURK_CUDA_TRY(cudaMemset(g_pool.d_bad, 0, sizeof(int)));
+    // the slot streams are non-blocking (they do not order against the legacy stream): clear the counter and wait for it
+    // before any chunk's range check can add to it
+    LURK_CUDA_TRY(cudaMemsetAsync(g_pool.d_bad, 0, sizeof(int), nullptr));
+    LURK_CUDA_TRY(cudaStreamSynchronize(nullptr));
     const size_t nchunks = (n + chunk - 1) / chunk;
     const int nslots = nchunks >= 3 ? 3 : (int)nchunks;
     for (int k = 0; k < nslots; k++) LURK_TRY(slot_reserve(g_pool.slot[k], chunk * in_per, chunk * out_per));

@@ -432,21 +432,31 @@ int device_consts(PoseidonInstance<F> &inst, const F **out) {
     return LURK_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize opt-in, once per (kernel instantiation, device).  A failed attempt is not
+// remembered, so a transient error is retried by the next launch; any number of devices.
+struct SmemOptIn {
+    std::mutex mu;
+    std::vector<int> done;
+    template <class K>
+    int ensure(K kern, size_t bytes) {
+        int dev = 0;
+        LURK_CUDA_TRY(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> g(mu);
+        for (int d : done) if (d == dev) return LURK_OK;
+        LURK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        done.push_back(dev);
+        return LURK_OK;
+    }
+};
+
 template <class F, int ARITY, bool WITNESS>
 int launch_one(const F *d_consts, const PoseidonInstance<F> &inst, const void *d_pre, size_t n, void *d_out,
                       const uint64_t *d_offs, int in_fmt, int out_fmt, int grid, int block, cudaStream_t s) {
     constexpr int T = ARITY + 1;
     constexpr int BIG = ARITY >= 6 ? 384 : 512;
     auto kern = poseidon_kernel<F, ARITY, WITNESS>;
-    static std::once_flag once[16];   // per device: opt in to the large dynamic shared-memory carve-out
-    int dev = 0;
-    LURK_CUDA_TRY(cudaGetDevice(&dev));
-    cudaError_t attr_err = cudaSuccess;
-    std::call_once(once[dev & 15], [&] {
-        size_t max_smem = (size_t)inst.layout.flat_len * sizeof(F) + (size_t)T * 2 * BIG * sizeof(uint4);
-        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-    });
-    LURK_CUDA_TRY(attr_err);
+    static SmemOptIn optin;           // per device: opt in to the large dynamic shared-memory carve-out
+    LURK_TRY(optin.ensure(kern, (size_t)inst.layout.flat_len * sizeof(F) + (size_t)T * 2 * BIG * sizeof(uint4)));
     size_t smem = (size_t)inst.layout.flat_len * sizeof(F) + (size_t)T * 2 * block * sizeof(uint4);
     kern<<<grid, block, smem, s>>>(d_consts, inst.layout, inst.params.domain_tag, (const F *)d_pre, n, (F *)d_out, d_offs, in_fmt, out_fmt);
     LURK_CUDA_TRY(cudaGetLastError());
@@ -472,19 +482,17 @@ int launch_arity(const void *d_pre, size_t n, void *d_out, const uint64_t *d_off
         const unsigned grid = (unsigned)((warps + 3) / 4);
         auto kern = poseidon_warp_kernel<F, ARITY, WITNESS>;
         const size_t smem = (size_t)inst.layout.flat_len * sizeof(F);
-        static std::once_flag once[16];
-        int dev = 0;
-        LURK_CUDA_TRY(cudaGetDevice(&dev));
-        cudaError_t attr_err = cudaSuccess;
-        std::call_once(once[dev & 15], [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
-        LURK_CUDA_TRY(attr_err);
+        static SmemOptIn optin;
+        LURK_TRY(optin.ensure(kern, smem));
         kern<<<grid, 128, smem, s>>>(d_consts, inst.layout, inst.params.domain_tag, (const F *)d_pre, n, (F *)d_out, d_offs, in_fmt, out_fmt);
         LURK_CUDA_TRY(cudaGetLastError());
         return LURK_OK;
     }
-    // medium batches: thread-per-sponge, single warps spread over the SMs
-    int grid = (int)((n + 31) / 32);
-    return launch_one<F, ARITY, WITNESS>(d_consts, inst, d_pre, n, d_out, d_offs, in_fmt, out_fmt, grid, 32, s);
+    // medium batches: thread-per-sponge; the widest CTA that still gives every SM one (each CTA stages the 20-40 KB of
+    // constants once, so one-warp CTAs are used only when there are fewer warps than SMs x 2)
+    const int block = n >= (size_t)sms * 128 ? 128 : (n >= (size_t)sms * 64 ? 64 : 32);
+    int grid = (int)((n + block - 1) / block);
+    return launch_one<F, ARITY, WITNESS>(d_consts, inst, d_pre, n, d_out, d_offs, in_fmt, out_fmt, grid, block, s);
 }
 
 template <class F, bool WITNESS>

@@ -266,6 +266,60 @@ def slot_witness(field_id, preimage):
     return [x % FIELD_MODULUS[field_id] for x in preimage] + aux + [d]
 
 
+# ---------------------------------------------------------------- Nova random oracle (Arecibo PoseidonRO)
+# Arecibo (git dependency `nova`, branch dev, not in tree) instantiates its RO as neptune's SAFE sponge over
+# PoseidonConstants<F, U24> = Sponge::api_constants(Strength::Standard): width 25, simplex mode, IO pattern
+# [Absorb(n), Squeeze(1)], the squeezed element truncated to its low `num_bits` bits and re-read in the other
+# field of the cycle.  Call sites in the reference: every `prove_step` (src/proof/nova.rs:286-293).  Restated
+# from the public crates; no golden challenge exists in the reference => parity unpinned.
+RO_RATE = 24
+
+
+def sponge_io_tag(n_absorb, n_squeeze=1, domain_separator=0):
+    """neptune sponge::api::IOPattern::value: polynomial hash in wrapping u128 with base 2^128 - 159"""
+    mask = (1 << 128) - 1
+    x = (0 - 159) & mask
+    x_i, state = 1, 0
+    for v in (n_absorb + (1 << 31), n_squeeze, domain_separator):
+        x_i = x_i * x & mask
+        state = (state + x_i * v) & mask
+    return state
+
+
+def poseidon_permute(field_id, state):
+    """textbook permutation of a full state (width len(state)); Neptune constants of that width"""
+    t = len(state)
+    P = params(field_id, t - 1)
+    p, rf, rp, rc, mds = P["p"], P["rf"], P["rp"], P["rc"], P["mds"]
+    s = [x % p for x in state]
+    half = rf // 2
+    for r in range(rf + rp):
+        s = [(a + b) % p for a, b in zip(s, rc[r * t:(r + 1) * t])]
+        if r < half or r >= half + rp:
+            s = [pow(x, 5, p) for x in s]
+        else:
+            s[0] = pow(s[0], 5, p)
+        s = vec_mat(s, mds, p)
+    return s
+
+
+def ro_squeeze(base_field_id, absorbed, num_bits=128):
+    """PoseidonRO::squeeze: capacity element = IO tag, absorbed elements in the rate, one permutation, element 1,
+    low num_bits bits.  Returns (challenge integer, full squeezed element)."""
+    assert 1 <= len(absorbed) <= RO_RATE
+    p = FIELD_MODULUS[base_field_id]
+    state = [sponge_io_tag(len(absorbed)) % p] + [a % p for a in absorbed] + [0] * (RO_RATE - len(absorbed))
+    h = poseidon_permute(base_field_id, state)[1]
+    return h & ((1 << num_bits) - 1), h
+
+
+def nifs_absorb_list(pp_digest, comm_W2, X2, comm_T):
+    """what Arecibo's NIFS::prove absorbs: pp digest, U2 = (comm_W, X), comm_T; points as (x, y, is_infinity)"""
+    def pt(P):
+        return [0, 0, 1] if P is None else [P[0], P[1], 0]
+    return [pp_digest] + pt(comm_W2) + list(X2) + pt(comm_T)
+
+
 # ---------------------------------------------------------------- bit decomposition slot
 def bitdecomp_witness(field_id, x):
     """bellpepper-core AllocatedNum::to_bits_le_strict aux allocation order, preceded by the

@@ -18,6 +18,7 @@ static int run(int op, const uint8_t *a, const uint8_t *b, uint8_t *out) {
         case 4: r = x.neg(); break;
         case 5: r = x.pow5(); break;
         case 6: r = x.sqr(); break;
+        case 7: r = x.inv_vartime(); break;
         default: return -2;
     }
     r = r.to_canonical();

@@ -99,6 +99,11 @@ def test_limb_arithmetic_against_bigints(fieldlib, spec, field):
     for a, _ in cases[:12]:
         fieldlib.fe_test_op(field, 3, a.to_bytes(32, "little"), bytes(32), out)
         assert int.from_bytes(out.raw, "little") == pow(a, p - 2, p)
+    # binary-GCD inversion (the one-thread normalisation on the fold's critical chain): every case incl. 0 -> 0
+    for a, b in cases:
+        for x in (a, b):
+            fieldlib.fe_test_op(field, 7, x.to_bytes(32, "little"), bytes(32), out)
+            assert int.from_bytes(out.raw, "little") == pow(x, p - 2, p), (field, x)
     # lazy dot products (one reduction per MDS row)
     for trial in range(300):
         k = rnd.randint(1, 15)
