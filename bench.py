@@ -1,29 +1,31 @@
 #!/usr/bin/env python3
 """bench.py -- Lurk reduction iterations proved per second on the GPU hot path (BASELINE.json metric).
 
-Workload: the per-fold GPU work of `benches/fibonacci.rs` at rc = 100 (Nova IVC, BN254 /
-Grumpkin cycle as the reference bench really runs -- SURVEY.md D1), composed from the kernels of SURVEY.md 8(a) exactly
-as RecursiveSNARK::prove_step uses them, on synthetic inputs of the real shapes:
-    K3  slot witnesses: 1400 Hash4 + 600 Hash8 + 100 Commitment Poseidon witnesses + 300 bit decompositions per step
-        (src/lem/eval.rs:1960-1964, 14/6/1/3 slots x rc frames) written into the step witness W2
-    K4  comm_W = commit(W2),  |W| = rc * 9119 = 911 900 scalars (src/lem/eval.rs:1966)
-    K5  6 CSR SpMV (A,B,C x z1,z2), cross term T, rows = rc * 11141 = 1 114 100 (src/lem/eval.rs:1967)
-    K4  comm_T = commit(T)
-    K5  fold W <- W1 + r W2, E <- E1 + r T with r derived from the commitments
-    K4  the two commitments of the ~10^4-constraint secondary circuit on Grumpkin
-A "step" is one fold = rc iterations.  The reference's end-to-end prover cannot be built here (Rust, no toolchain; LEM
-synthesis and the Nova RO stay on the CPU and are out of scope), so this is the composed-kernel form SURVEY.md 8(d)
-allows; `config.composed` says so.  R1CS matrices are synthetic (frame-local columns, 1-3 non-zeros per row).
+Workload `fib` (default): the per-fold GPU work of `benches/fibonacci.rs` at rc = 100 (Nova IVC, BN254 / Grumpkin cycle
+as the reference bench really runs -- SURVEY.md D1), driven ONLY through the fold context of the C ABI
+(lurk_fold_ctx_*, include/lurk_b200.h), i.e. what RecursiveSNARK::prove_step does with the step circuit's witness inside
+Arecibo's NIFS::prove, on synthetic inputs of the real shapes:
+    stage A  H2D of the step's inputs (slot preimages, LEM-body aux, public IO);  1400 Hash4 + 600 Hash8 + 100 Commitment
+             Poseidon slot witnesses + 300 bit decompositions written in place into W2 (src/lem/eval.rs:1960-1964);
+             comm_W2 = commit(W2), |W| = rc * 9119 = 911 900 (eval.rs:1966);  A z2, B z2, C z2
+    stage B  A z1, B z1, C z1;  cross term T over rc * 11141 = 1 114 100 rows (eval.rs:1967);  comm_T = commit(T);
+             Poseidon-sponge random oracle -> r;  (W, u, X) += r (W2, 1, X2), E += r T;  comm_W += r comm_W2, comm_E += r comm_T
+    + the same fold of the ~10^4-constraint secondary circuit on Grumpkin (second context)
+A "step" is one fold = rc iterations.  The R1CS is synthetic but SATISFIABLE by construction (per frame 1311 product rows
+that define the LEM-body aux from slot-witness columns, 9830 linear rows), so the folded running instance is CHECKED
+before timing: relaxed R1CS residual = 0 and commit(W), commit(E) equal the folded commitments (on the device), and one
+full-size fold's comm_W2, comm_T and challenge are compared with the CPU oracle.  Not included (CPU work of the
+reference that is out of scope): LEM synthesis of the body aux, Nova's augmented-circuit synthesis.
 
-N > 1 (torchrun, one process per GPU, NCCL): weak scaling -- rc = 100 * N frames, the witness, the matrices (by rows)
-and the commitment key (contiguous base shards) are split by frame across ranks; the only exchange is one all-gather
-of the two 96-byte partial commitments per step followed by local point additions.
+N > 1 (torchrun, one process per GPU): frames, witness, matrix rows and the commitment key are split by frame across ranks;
+the only exchange is the two partial commitments per step, written peer-to-peer into every rank's exchange buffer over
+NVLink by the challenge kernel itself (no NCCL call, no host hop on the chain).  --scaling weak: rc = 100 * N (the
+reference layout of a larger step circuit); --scaling strong: ONE rc = 100 fold, its 2^21-point key split N ways.
 
-`--impl reference` times the CPU restatement of the same step (oracle/, OpenMP on all host cores): the reference's own
-prover is Rust and cannot run in this image.
+`--impl reference` times the CPU restatement of the same step (oracle/, all host threads): the reference's own prover
+is Rust and cannot be built in this image.
 """
 import argparse
-import hashlib
 import json
 import os
 import sys
@@ -40,10 +42,15 @@ AUX_PER_FRAME = 9119          # src/lem/eval.rs:1966
 CONS_PER_FRAME = 11141        # src/lem/eval.rs:1967
 SLOTS = [(4, 14), (8, 6), (3, 1)]   # (arity, slots per frame); hash6 has no slots (eval.rs:1960-1964)
 BITDECOMP_PER_FRAME = 3
+SLOT_ELEMS = 7808             # 14*293 + 6*396 + 268 + 3*354 (multiframe.rs:991-1016)
+GLUE_PER_FRAME = AUX_PER_FRAME - SLOT_ELEMS     # 1311 LEM-body aux
 SECONDARY_N = 10_000          # secondary-circuit witness / constraint count (order of magnitude)
-FIELD, CURVE, CURVE2 = 0, 0, 1   # BN254 Fr; BN254 G1 primary, Grumpkin secondary
+CURVE, CURVE2 = 0, 1          # BN254 G1 primary (witness field Fr), Grumpkin secondary (witness field Fq)
 LIVE_SLOT_FRACTION = 0.25     # most slots of a frame are dummies (multiframe.rs:553-577)
-PREFETCH_DEPTH = 1            # stage A (slot witnesses, commit(W), Az2..) runs this many steps ahead of the fold
+PP_DIGEST = 0x2c5d1f0a9b8e7d6c5b4a39281706f5e4d3c2b1a0918273645546372819
+P_FR = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+P_FQ = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+METRIC = "Lurk iterations proved/sec (fib rc=100, Nova IVC)"
 
 
 def rand_elements(rng, count, shape="uniform"):
@@ -59,16 +66,98 @@ def rand_elements(rng, count, shape="uniform"):
     return raw.reshape(-1)
 
 
-def synthetic_r1cs(rng, rows, cols, mean_nnz):
-    """CSR with 1..(2*mean-1) non-zeros per row, small coefficients; canonical values"""
-    hi = int(2 * mean_nnz)
-    nnz_per = rng.integers(1, hi, size=rows)
-    row_ptr = np.concatenate([[0], np.cumsum(nnz_per)]).astype(np.uint64)
-    nnz = int(row_ptr[-1])
-    col = rng.integers(0, cols, size=nnz).astype(np.uint32)
-    val = np.zeros((nnz, 32), dtype=np.uint8)
-    val[:, 0] = rng.integers(1, 8, size=nnz, dtype=np.uint8)
-    return row_ptr, col, val.reshape(-1)
+def small_vals(rng, n):
+    val = np.zeros((n, 32), dtype=np.uint8)
+    val[:, 0] = rng.integers(1, 8, size=n, dtype=np.uint8)
+    return val.reshape(-1)
+
+
+def step_circuit(seed, frames, slot_elems=SLOT_ELEMS, glue=GLUE_PER_FRAME, cons=CONS_PER_FRAME, n_x=2):
+    """Synthetic R1CS in the shape of the Lurk step circuit, satisfiable by construction (same rule as
+    oracle/nifs.py:synthetic_step_circuit, vectorised): per frame `glue` product rows (a . slots)(b . slots) = glue_g and
+    cons - glue linear rows (a . z) u = (a . z).  Columns: frame-major W, then u, then X.  Values canonical small ints.
+    Returns [(row_ptr, col, val)] x 3, n_w, rows, product_rows (global row index of every product row, frame-major)."""
+    rng = np.random.default_rng(seed)
+    per = slot_elems + glue
+    n_w, rows = frames * per, frames * cons
+    lin = cons - glue
+    frame_of_row = np.repeat(np.arange(frames, dtype=np.int64), cons)
+    local = np.tile(np.arange(cons, dtype=np.int64), frames)
+    is_prod = local < glue
+
+    def random_rows(nnz_hi_prod, nnz_hi_lin):
+        nnz = np.where(is_prod, rng.integers(1, nnz_hi_prod + 1, size=rows), rng.integers(1, nnz_hi_lin + 1, size=rows))
+        rp = np.concatenate([[0], np.cumsum(nnz)]).astype(np.uint64)
+        r_of = np.repeat(np.arange(rows), nnz)
+        span = np.where(is_prod[r_of], slot_elems, per)
+        col = frame_of_row[r_of] * per + (rng.random(r_of.size) * span).astype(np.int64)
+        return rp, col.astype(np.uint32), small_vals(rng, r_of.size)
+
+    A = random_rows(3, 3)
+    # B: product rows as A (1..2 slot columns); linear rows = the u column with coefficient 1
+    nnz = np.where(is_prod, rng.integers(1, 3, size=rows), 1)
+    rp = np.concatenate([[0], np.cumsum(nnz)]).astype(np.uint64)
+    r_of = np.repeat(np.arange(rows), nnz)
+    col = np.where(is_prod[r_of], frame_of_row[r_of] * per + (rng.random(r_of.size) * slot_elems).astype(np.int64), n_w)
+    val = small_vals(rng, r_of.size).reshape(-1, 32)
+    val[~is_prod[r_of]] = 0
+    val[~is_prod[r_of], 0] = 1
+    B = (rp, col.astype(np.uint32), val.reshape(-1))
+    # C: product rows = the glue column they define; linear rows = their A row
+    a_rp, a_col, a_val = A
+    a_nnz = np.diff(a_rp.astype(np.int64))
+    c_nnz = np.where(is_prod, 1, a_nnz)
+    c_rp = np.concatenate([[0], np.cumsum(c_nnz)]).astype(np.uint64)
+    c_col = np.empty(int(c_rp[-1]), dtype=np.uint32)
+    c_val = np.zeros((int(c_rp[-1]), 32), dtype=np.uint8)
+    a_r_of = np.repeat(np.arange(rows), a_nnz)
+    keep = ~is_prod[a_r_of]
+    c_r_of = np.repeat(np.arange(rows), c_nnz)
+    lin_mask = ~is_prod[c_r_of]
+    c_col[lin_mask] = a_col[keep]
+    c_val[lin_mask] = a_val.reshape(-1, 32)[keep]
+    prod_rows = np.nonzero(is_prod)[0]
+    c_col[~lin_mask] = (frame_of_row[prod_rows] * per + slot_elems + local[prod_rows]).astype(np.uint32)
+    c_val[~lin_mask, 0] = 1
+    C = (c_rp, c_col, c_val.reshape(-1))
+    return [A, B, C], n_w, rows, prod_rows
+
+
+def slot_offsets(frames):
+    """element offset of every slot block inside W, in the reference's frame layout (multiframe.rs:635-712)"""
+    import lurk_beta_b200 as L
+    lib = L._capi.lib()
+    out, cur = [], 0
+    f = np.arange(frames, dtype=np.uint64)[:, None] * AUX_PER_FRAME
+    for arity, per_frame in SLOTS:
+        blk = lib.lurk_poseidon_witness_block(0, arity)
+        out.append((arity, (f + cur + np.arange(per_frame, dtype=np.uint64)[None, :] * blk).reshape(-1)))
+        cur += per_frame * blk
+    blk = lib.lurk_bitdecomp_witness_block(0)
+    out.append((0, (f + cur + np.arange(BITDECOMP_PER_FRAME, dtype=np.uint64)[None, :] * blk).reshape(-1)))
+    assert cur + BITDECOMP_PER_FRAME * blk == SLOT_ELEMS
+    return out
+
+
+def to_mont(buf, p):
+    """canonical 32-byte elements -> Montgomery bytes (host, setup only)"""
+    b = np.ascontiguousarray(buf, dtype=np.uint8).tobytes()
+    R = 1 << 256
+    return np.frombuffer(b"".join((int.from_bytes(b[i:i + 32], "little") * R % p).to_bytes(32, "little") for i in range(0, len(b), 32)),
+                         dtype=np.uint8).copy()
+
+
+def workload_config(world, scaling):
+    frames = RC * world if scaling == "weak" else RC
+    return {"workload": "fib rc=100 Nova IVC fold step on BN254/Grumpkin (benches/fibonacci.rs, configs[0]/metric config)",
+            "composed": "per fold, through lurk_fold_ctx_*: H2D of slot preimages + LEM-body aux; 2100 Poseidon slot witnesses + 300 bit-decomps "
+                        "per 100 frames; commit(W) 911900 terms; 6 SpMV + cross term over 1114100 rows; commit(T); Poseidon-sponge RO challenge; "
+                        "fold of (W,u,X), E and both commitments; the same fold of a 10^4-constraint secondary circuit on Grumpkin. "
+                        "LEM synthesis / augmented-circuit synthesis / reference Rust prover not included",
+            "frames_per_step": frames, "scaling": scaling,
+            "commitment_key": "2^21 synthetic BN254 G1 points per 100 frames ([i+1]G), sharded by frame; fixed-base window tables built once",
+            "l2": "inputs per step (128 MiB key, 1.7 GB window table, 64 MiB of vectors, 140 MiB CSR) exceed the 126 MB L2",
+            "parallelism": f"frames/bases sharded over {world} GPU(s); partial commitments exchanged through NVLink peer memory inside the challenge kernel"}
 
 
 class ClockSampler:
@@ -83,7 +172,6 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists plain indices
             vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
             ids = [int(x) for x in vis.split(",") if x.strip().isdigit()]
             phys = ids[self.index] if self.index < len(ids) else self.index
@@ -119,153 +207,221 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------- GPU arm
 class FoldStepGPU:
-    """one rank's share of the fold step: rc = RC frames, device-resident state"""
+    """one rank's share of the fold step, driven through the C-ABI fold context"""
 
-    def __init__(self, rank, world, seed=0x6c75726b, fixed_base=True):
+    def __init__(self, rank, world, scaling="weak", latency_sms=0, seed=0x6c75726b):
         import torch
         import lurk_beta_b200 as L
         self.torch, self.L = torch, L
-        self.lib = L._capi.lib()
         self.rank, self.world = rank, world
-        rng = np.random.default_rng(seed + rank)
-        self.nW = RC * AUX_PER_FRAME
-        self.nT = RC * CONS_PER_FRAME
-        self.n_key = 1 << 21                       # Arecibo pads the key to the next power of two (SURVEY.md D3)
-        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-        self.dev = dev
-        # ---- commitment keys: this rank's contiguous shard of a (world * 2^21)-point key
-        bases = L.synthetic_bases(CURVE, self.n_key, start=rank * self.n_key, fmt=L.FMT_MONTGOMERY)
-        self.ck = L.CommitmentKey(CURVE, bases, fmt=L.FMT_MONTGOMERY)
-        if fixed_base:
-            self.ck.precompute()      # the key is fixed per (rc, Lang): window multiples built once (1.7 GB of HBM)
-        self.ck.set_profiling(True)
-        del bases
-        self.ck2 = L.CommitmentKey(CURVE2, L.synthetic_bases(CURVE2, 1 << 14, fmt=L.FMT_MONTGOMERY), fmt=L.FMT_MONTGOMERY)
-        # ---- slot preimages (host, pinned: what the CPU gather hands over every step).  W is laid out as the reference
-        # lays it out (synthesize_frames_parallel, src/lem/multiframe.rs:635-712): per frame [14 Hash4 blocks | 6 Hash8 |
-        # 1 Commitment | 3 BitDecomp | 1311 LEM-body aux] = 9119 elements; the kernels scatter each block to its place.
-        self.slot_pre_host, self.slot_pre_dev = {}, {}
-        self.slot_layout = []
-        self.bd_block = self.lib.lurk_bitdecomp_witness_block(FIELD)
-        frame_off = 0
-        for arity, per_frame in SLOTS:
-            n = RC * per_frame
-            pre = rand_elements(rng, n * arity).reshape(n, arity * 32)
-            dummy = rng.random(n) >= LIVE_SLOT_FRACTION
-            pre[dummy] = 0
-            blk = self.lib.lurk_poseidon_witness_block(FIELD, arity)
-            self.slot_pre_host[arity] = torch.from_numpy(pre.reshape(-1)).pin_memory()
-            self.slot_pre_dev[arity] = [self.slot_pre_host[arity].cuda() for _ in range(PREFETCH_DEPTH + 1)]   # one per in-flight step
-            offs = (np.arange(RC, dtype=np.uint64)[:, None] * AUX_PER_FRAME + frame_off + np.arange(per_frame, dtype=np.uint64)[None, :] * blk).reshape(-1)
-            self.slot_layout.append((arity, n, torch.from_numpy(offs).cuda(), blk))
-            frame_off += per_frame * blk
-        nbd = RC * BITDECOMP_PER_FRAME
-        self.bd_host = torch.from_numpy(rand_elements(rng, nbd, "witness")).pin_memory()
-        self.bd_dev = [self.bd_host.cuda() for _ in range(PREFETCH_DEPTH + 1)]
-        self.bd_n = nbd
-        offs = (np.arange(RC, dtype=np.uint64)[:, None] * AUX_PER_FRAME + frame_off + np.arange(BITDECOMP_PER_FRAME, dtype=np.uint64)[None, :] * self.bd_block).reshape(-1)
-        self.bd_offs = torch.from_numpy(offs).cuda()
-        frame_off += BITDECOMP_PER_FRAME * self.bd_block
-        self.slot_per_frame = frame_off                # 7808 slot-witness elements per frame
-        assert self.slot_per_frame == 7808
-        self.glue_per_frame = AUX_PER_FRAME - self.slot_per_frame
-        # ---- witness vectors (Montgomery, device resident).  z = (W, u, X0, X1); W1 / W2 are views into z1 / z2 so the
-        # SpMVs read them in place.  The fresh-instance side (W2, Az2..Cz2) is double buffered: slot witnesses and
-        # commit(W) of step i+1 are chain independent (SURVEY.md H5) and run ahead of the fold of step i, as the
-        # reference's witness thread does (src/proof/nova.rs:297-326).
-        glue = RC * self.glue_per_frame
-        self.glue_host = torch.from_numpy(rand_elements(rng, glue, "witness")).pin_memory()
-        self.ncols = self.nW + 3
-        tail = dev(rand_elements(rng, 3))
-        self.z1 = torch.empty(self.ncols * 32, dtype=torch.uint8, device="cuda")
-        self.z1[:self.nW * 32] = dev(rand_elements(rng, self.nW))
-        self.z1[self.nW * 32:] = tail
-        self.W1 = self.z1[:self.nW * 32]
-        self.z2, self.W2 = [], []
-        for _ in range(PREFETCH_DEPTH + 1):
-            z = torch.empty(self.ncols * 32, dtype=torch.uint8, device="cuda")
-            z[:self.nW * 32].view(RC, AUX_PER_FRAME * 32)[:, self.slot_per_frame * 32:] = self.glue_host.cuda().view(RC, -1)
-            z[self.nW * 32:] = tail
-            self.z2.append(z)
-            self.W2.append(z[:self.nW * 32])
-        self.E1 = dev(rand_elements(rng, self.nT))
-        self.mats = []
-        for mean in (2.0, 2.0, 1.5):
-            rp, col, val = synthetic_r1cs(rng, self.nT, self.ncols, mean)
-            self.mats.append((dev(rp), dev(col), dev(val), int(rp[-1])))
-        self.u1 = rand_elements(rng, 1)
-        self.u2 = rand_elements(rng, 1)
-        self.W_sec = dev(rand_elements(rng, SECONDARY_N, "witness"))
-        self.T_sec = dev(rand_elements(rng, SECONDARY_N))
-        self.launches = 0
-        self.acc_ms = []
-        self.h2d_bytes = sum(t.numel() for t in self.slot_pre_host.values()) + self.bd_host.numel() + self.glue_host.numel()
-        self.d2h_bytes = 0
+        M = L.FMT_MONTGOMERY
+        total_frames = RC * world if scaling == "weak" else RC
+        f0, f1 = (total_frames * rank) // world, (total_frames * (rank + 1)) // world
+        self.frames = f1 - f0
+        # the same circuit on every rank count: rows / columns of this rank's frames (frame-local columns + the (u, X) tail)
+        mats, self.nW, self.nT, prod_rows = step_circuit(seed + 1000 * rank, self.frames)
+        self.prod_rows = prod_rows
+        # ---- commitment key: this rank's slices of the global key [i+1]G in the reference's layout (W index = frame * 9119 + j,
+        # T / E index = frame * 11141 + j).  One resident 2^21-point key serves both when nothing is sharded.
+        if world == 1:
+            self.ck_w = self.ck_t = L.CommitmentKey(CURVE, L.synthetic_bases(CURVE, 1 << 21, fmt=M), fmt=M)
+        else:
+            self.ck_w = L.CommitmentKey(CURVE, L.synthetic_bases(CURVE, self.nW, start=f0 * AUX_PER_FRAME, fmt=M), fmt=M)
+            self.ck_t = L.CommitmentKey(CURVE, L.synthetic_bases(CURVE, self.nT, start=f0 * CONS_PER_FRAME, fmt=M), fmt=M)
+        self.ctx = L.NovaFoldContext(CURVE, self.ck_w, self.nW, 2, mats, depth=2, fmt=L.FMT_CANONICAL, ck_t=self.ck_t, world=world, rank=rank,
+                                     latency_sms=latency_sms)
+        self.mats = mats
+        self.batch = [(arity, self.ctx.add_slot_batch(arity, offs)) for arity, offs in slot_offsets(self.frames)]
+        self.ctx.set_spans([(SLOT_ELEMS, GLUE_PER_FRAME, AUX_PER_FRAME, self.frames)])
+        # ---- secondary circuit (Grumpkin): whole witness from the host, replicated on every rank
+        mats2, self.nW2, self.nT2, prod2 = step_circuit(seed + 7, 1, slot_elems=SECONDARY_N - 1500, glue=1500, cons=SECONDARY_N)
+        self.ck2 = L.CommitmentKey(CURVE2, L.synthetic_bases(CURVE2, 1 << 14, fmt=M), fmt=M)
+        self.ctx2 = L.NovaFoldContext(CURVE2, self.ck2, self.nW2, 2, mats2, depth=2, fmt=L.FMT_CANONICAL)
+        self.ctx2.set_spans([(0, self.nW2, self.nW2, 1)])
+        self.mats2, self.prod2 = mats2, prod2
+        # ---- synthetic inputs of one step, written once into the pinned buffers of both fresh-instance buffers (Montgomery,
+        # the in-memory form of halo2curves); the X / RO constants are identical on every rank (the challenge must agree)
+        rng = np.random.default_rng(seed + 17 * rank)
+        common = np.random.default_rng(seed + 99)
+        self.X2 = [int(common.integers(1, 2**62)) * int(common.integers(1, 2**62)) for _ in range(2)]
+        self.X2s = [int(common.integers(1, 2**62)) * int(common.integers(1, 2**62)) for _ in range(2)]
+        pre = {}
+        for arity, idx in self.batch:
+            n = self.frames * (dict(SLOTS).get(arity, BITDECOMP_PER_FRAME))
+            if arity:
+                x = rand_elements(rng, n * arity).reshape(n, arity * 32)
+                x[rng.random(n) >= LIVE_SLOT_FRACTION] = 0
+                pre[idx] = x.reshape(-1)
+            else:
+                pre[idx] = rand_elements(rng, n, "witness")
+        ro = self._ro_consts(self.X2, P_FQ)
+        # every input is handed over in Montgomery form (the in-memory form of halo2curves' field types); the random bytes
+        # below are < p, i.e. valid Montgomery representatives of uniformly random elements
+        for b in range(2):
+            for idx, x in pre.items():
+                self.ctx.host_buffer(b, idx)[:] = x
+            self.ctx.host_buffer(b, L._capi.FOLD_BUF_X2)[:] = to_mont(self._pack(self.X2), P_FR)
+            self.ctx.host_buffer(b, L._capi.FOLD_BUF_RO)[:] = ro
+        # run the slot kernels once to learn the slot columns, then define the LEM-body aux from them (product rows)
+        self._derive_glue(self.ctx, self.mats, self.prod_rows, self.nW, self.nT, P_FR, slots=True)
+        w2 = to_mont(rand_elements(rng, self.nW2, "witness"), P_FQ)
+        for b in range(2):
+            self.ctx2.host_buffer(b, L._capi.FOLD_BUF_GLUE)[:] = w2
+            self.ctx2.host_buffer(b, L._capi.FOLD_BUF_X2)[:] = to_mont(self._pack(self.X2s), P_FQ)
+            self.ctx2.host_buffer(b, L._capi.FOLD_BUF_RO)[:] = self._ro_consts(self.X2s, P_FR)
+        self._derive_glue(self.ctx2, self.mats2, self.prod2, self.nW2, self.nT2, P_FQ, slots=False)
+        self.h2d_bytes = sum(self.ctx.host_buffer(0, w).size for w in [i for _, i in self.batch] + [-1, -2, -3]) + \
+            sum(self.ctx2.host_buffer(0, w).size for w in (-1, -2, -3))
+        self.d2h_bytes = 2 * 448                         # the two result records
+        self.step_index = 0
+        self.started = False
         torch.cuda.synchronize()
 
-    def _setup(self):
-        from lurk_beta_b200.fold import NovaFoldPipeline, SlotBatch
-        t = self.torch
-        self.pipe = NovaFoldPipeline(t, FIELD, CURVE, self.ck, self.nW, self.nT, [(rp, col, val) for rp, col, val, _ in self.mats],
-                                     self.u1, self.u2, self.z1, self.E1, self.z2, world=self.world)
-        self.slot_batches = []
-        for b in range(PREFETCH_DEPTH + 1):
-            sb = [SlotBatch(a, n, 0, self.slot_pre_dev[a][b], d_offsets=offs) for a, n, offs, _blk in self.slot_layout]
-            sb.append(SlotBatch(0, self.bd_n, 0, self.bd_dev[b], d_offsets=self.bd_offs))
-            self.slot_batches.append(sb)
-        self.sS = t.cuda.Stream(priority=-1)               # secondary-circuit commitments (tiny: let them through at once)
-        self.ck2b = self.ck2.clone()
-        self.prefetched = -1                               # last step index whose stage A has been enqueued
-        self.step_index = 0
-
-    def stage_inputs(self, b):
-        """host -> device copy of one step's inputs from pinned memory (the e2e leg), into buffer b"""
-        for arity, h in self.slot_pre_host.items():
-            self.slot_pre_dev[arity][b].copy_(h, non_blocking=True)
-        self.bd_dev[b].copy_(self.bd_host, non_blocking=True)
-        # LEM-body aux of every frame (strided 2-D copy: 1311 elements after each frame's 7808 slot elements)
-        self.W2[b].view(RC, AUX_PER_FRAME * 32)[:, self.slot_per_frame * 32:].copy_(self.glue_host.view(RC, -1), non_blocking=True)
-
     @staticmethod
-    def challenge(cw, ct):
-        """stand-in for the Poseidon-sponge RO on the CPU: 128 bits derived from the commitments"""
-        r = np.zeros(32, dtype=np.uint8)
-        r[:16] = np.frombuffer(hashlib.sha256(cw.tobytes() + ct.tobytes()).digest()[:16], dtype=np.uint8)
-        return r
+    def _pack(vals):
+        return np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), dtype=np.uint8).copy()
 
-    def step(self, staged=False, group=None):
-        """One fold.  Stage A of the next step is enqueued before this step's commitments are collected, so its slot
-        witnesses / commit(W) fill the GPU while the host finishes this fold (lurk_beta_b200/fold.py)."""
-        if not hasattr(self, "pipe"):
-            self._setup()
-        L, M = self.L, self.L.FMT_MONTGOMERY
+    def _ro_consts(self, X2, p_base):
+        ro = np.zeros((24, 32), dtype=np.uint8)
+        for pos, v in ((0, PP_DIGEST), (4, X2[0]), (5, X2[1])):
+            ro[pos] = self._pack([v])
+        return to_mont(ro.reshape(-1), p_base)
+
+    def _derive_glue(self, ctx, mats, prod_rows, n_w, n_rows, p, slots):
+        """setup: make the fresh instance satisfy the circuit -- glue_g = (A_g . z)(B_g . z) for the product rows, computed with
+        the library's own SpMV / cross-term kernels on the device from the slot columns the slot kernels produce"""
+        t, L = self.torch, self.L
+        lib = L._capi.lib()
+        M = L.FMT_MONTGOMERY
+        field = 0 if p == P_FR else 1
+        ctx.stage_a(0, fmt=M)          # with the glue still zero: fills the slot columns of W2 / uploads the dense witness
+        ctx.sync()
+        z2 = ctx.device_view(0, L._capi.FOLD_BUF_W2)
+        dev = lambda a: t.from_numpy(np.ascontiguousarray(a)).cuda()
+        out = []
+        for rp, col, val in mats[:2]:
+            y = t.empty(n_rows * 32, dtype=t.uint8, device="cuda")
+            d = (dev(rp), dev(col), dev(to_mont_small(val, p)))
+            L._capi.check(lib.lurk_spmv_csr_dev(field, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), n_rows, z2.data_ptr(), y.data_ptr(), None))
+            out.append(y)
+        zero = t.zeros(n_rows * 32, dtype=t.uint8, device="cuda")
+        prod = t.empty(n_rows * 32, dtype=t.uint8, device="cuda")
+        z32 = np.zeros(32, dtype=np.uint8)
+        L._capi.check(lib.lurk_cross_term_dev(field, out[0].data_ptr(), zero.data_ptr(), zero.data_ptr(), zero.data_ptr(), out[1].data_ptr(),
+                                              zero.data_ptr(), L._capi.np_ptr(z32), L._capi.np_ptr(z32), n_rows, prod.data_ptr(), None))
+        t.cuda.synchronize()
+        glue = prod.view(n_rows, 32)[dev(prod_rows.astype(np.int64))].cpu().numpy().reshape(-1)
+        if slots:
+            for b in range(2):
+                ctx.host_buffer(b, L._capi.FOLD_BUF_GLUE)[:] = glue
+        else:
+            # secondary: the glue columns are the tail of the dense witness
+            per = n_w
+            g = glue.size // 32
+            for b in range(2):
+                ctx.host_buffer(b, L._capi.FOLD_BUF_GLUE)[(per - g) * 32:] = glue
+        del z2
+
+    # ------------------------------------------------------------------------------------------ the step loop
+    def start(self, staged):
+        """RecursiveSNARK::new on buffer 0, stage A of the first fold on buffer 1"""
+        for c in (self.ctx, self.ctx2):
+            c.stage_a(0, resident=not staged, fmt=self.L.FMT_MONTGOMERY)
+            c.init_running(0)
+            c.stage_a(1, resident=not staged, fmt=self.L.FMT_MONTGOMERY)
+        for c in (self.ctx, self.ctx2):
+            c.collect(0)
+        self.step_index = 1
+        self.uncollected = None
+        self.started = True
+
+    def step(self, staged):
+        """one fold: enqueue stage B of step i, collect step i-1's record, enqueue stage A of step i+1 into the freed buffer"""
         i = self.step_index
-        nb = PREFETCH_DEPTH + 1
-        b = i % nb
-        before = self.stage_inputs if staged else None
-        kA = self.pipe.launches_A
-        while self.prefetched < i + PREFETCH_DEPTH:              # keep stage A PREFETCH_DEPTH steps ahead
-            self.prefetched += 1
-            self.pipe.stage_a(self.prefetched % nb, self.slot_batches[self.prefetched % nb], before)
-            kA = self.pipe.launches_A
-        # secondary circuit (Grumpkin): two small commitments, independent of the primary fold
-        self.ck2.launch_device(self.W_sec.data_ptr(), SECONDARY_N, fmt=M, stream=self.sS.cuda_stream)
-        self.ck2b.launch_device(self.T_sec.data_ptr(), SECONDARY_N, fmt=M, stream=self.sS.cuda_stream)
-        cw, ct = self.pipe.stage_b(b, self.challenge)
-        self.ck2.finish()
-        self.ck2b.finish()
+        b = i & 1
+        self.ctx.stage_b_launch(b)
+        self.ctx2.stage_b_launch(b)
+        if self.uncollected is not None:
+            self.last = (self.ctx.collect(self.uncollected), self.ctx2.collect(self.uncollected))
+        self.uncollected = b
+        self.ctx.stage_a(b ^ 1, resident=not staged, fmt=self.L.FMT_MONTGOMERY)
+        self.ctx2.stage_a(b ^ 1, resident=not staged, fmt=self.L.FMT_MONTGOMERY)
         self.step_index = i + 1
-        self.acc_ms = self.pipe.accumulate_ms
-        self.launches = kA + self.pipe.launches_B + self.ck2.last_profile()[1] + self.ck2b.last_profile()[1]
-        self.d2h_bytes = 2 * 96 + 2 * 128 * 128 + 2 * 32 * 128   # result points + window sums read back by the 4 commitments
-        return cw, ct
 
     def drain(self):
-        """collect the commit(W) of a prefetched step that will not be folded (end of a timed region)"""
-        nb = PREFETCH_DEPTH + 1
-        while getattr(self, "prefetched", -1) >= self.step_index:
-            self.pipe.drain(self.prefetched % nb)
-            self.prefetched -= 1
+        """collect the last fold (the prefetched stage A of the step after it stays un-folded: it is extra work inside the region)"""
+        if self.uncollected is not None:
+            self.last = (self.ctx.collect(self.uncollected), self.ctx2.collect(self.uncollected))
+            self.uncollected = None
+        self.ctx.sync()
+        self.ctx2.sync()
+
+
+def to_mont_small(val, p):
+    """coefficients are small integers 1..7: Montgomery form through a table"""
+    R = 1 << 256
+    table = np.stack([np.frombuffer((k * R % p).to_bytes(32, "little"), dtype=np.uint8) for k in range(8)])
+    return table[np.ascontiguousarray(val, dtype=np.uint8).reshape(-1, 32)[:, 0]].reshape(-1)
+
+
+def verify_full_size(wl, rank):
+    """outside the timed region: (1) the device-side relaxed-R1CS check of the running instance after real folds, on every rank
+    (collective when the key is sharded); (2) rank 0 of an unsharded run: one full-size fold against the CPU oracle."""
+    out = {}
+    bad, okw, oke = wl.ctx.check_running()
+    bad2, okw2, oke2 = wl.ctx2.check_running()
+    out["relaxed_r1cs_bad_rows"] = int(bad) + int(bad2)
+    out["folded_commitments_open"] = bool(okw and oke and okw2 and oke2)
+    if wl.world == 1 and rank == 0:
+        from oracle import capi as oracle, spec, nifs   # checker only
+        L = wl.L
+        th = os.cpu_count() or 1
+        rec = wl.last[0]
+        ctx = wl.ctx
+        b = (wl.step_index - 1) & 1
+        R = 1 << 256
+        unmont = lambda buf, p: nifs.pack([x * pow(R, -1, p) % p for x in nifs.ints(buf)])
+        W2 = ctx.read_device(b, L._capi.FOLD_BUF_W2)[:wl.nW * 32]
+        T = ctx.read_device(0, L._capi.FOLD_BUF_T)
+        # Montgomery -> canonical on the device (library kernel), then host
+        t = wl.torch
+        lib = L._capi.lib()
+        both = t.from_numpy(np.concatenate([W2, T])).cuda()
+        L._capi.check(lib.lurk_convert_dev(0, both.data_ptr(), both.numel() // 32, L.FMT_CANONICAL, both.data_ptr(), None))
+        t.cuda.synchronize()
+        both = both.cpu().numpy()
+        W2c, Tc = both[:wl.nW * 32], both[wl.nW * 32:]
+        bases = oracle.gen_bases(CURVE, max(wl.nW, wl.nT))
+        want_w = oracle.msm(CURVE, bases, W2c, nthreads=th)
+        want_t = oracle.msm(CURVE, bases, Tc, nthreads=th)
+        r, h = spec.ro_squeeze(1, spec.nifs_absorb_list(PP_DIGEST, nifs.point_of(want_w), wl.X2, nifs.point_of(want_t)))
+        out["oracle_fold"] = {"comm_W": bool(np.array_equal(rec.comm_W, want_w)), "comm_T": bool(np.array_equal(rec.comm_T, want_t)),
+                              "challenge": int.from_bytes(rec.r.tobytes(), "little") == r, "terms": [wl.nW, wl.nT]}
+    return out
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from this round's committed ncu --set full capture (profiles/), or None"""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r2_ncu_full_msm_accumulate_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr = rows[0]
+        units = rows[1]
+        best = None
+        for row in rows[2:]:
+            rec = dict(zip(hdr, row))
+            if "msm_accumulate_kernel" not in rec.get("Kernel Name", ""):
+                continue
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v = float(rec[key].replace(",", ""))
+                u = units[hdr.index(key)].lower()
+                tot += v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+            best = tot
+        return best
+    except Exception:
+        return None
 
 
 def run_gpu(args):
@@ -289,20 +445,21 @@ def run_gpu(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    wl = FoldStepGPU(rank, world, fixed_base=not args.no_fixed_base)
+    wl = FoldStepGPU(rank, world, scaling=args.scaling, latency_sms=args.latency_sms)
+    wl.ctx.connect()          # exchange-buffer handles through the process group (setup only; the steps never call NCCL)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(staged, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            fn()
-        wl.drain()                        # the prefetched half-step is inside the timed region (it is extra work)
+            wl.step(staged)
+        wl.drain()
         torch.cuda.synchronize()          # work runs on several streams: close the region after all of them drained
         e1.record()
         barrier()
@@ -311,35 +468,33 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    def step_resident():
-        wl.step(staged=False)
-
-    def step_e2e():
-        wl.step(staged=True)
-
+    wl.start(staged=True)
     for _ in range(max(args.warmup, 3)):
-        step_e2e()
+        wl.step(True)
+    wl.drain()
+    verified = verify_full_size(wl, rank)          # after real folds, before timing
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    wl.pipe.accumulate_ms.clear()
-    ms = timed(step_resident, args.steps)
-    acc_ms = list(wl.pipe.accumulate_ms)
-    ms_e2e = timed(step_e2e, args.steps)
+    ms = timed(False, args.steps)
+    st = wl.ctx.stats()
+    st2 = wl.ctx2.stats()
+    ms_e2e = timed(True, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    # the same dominant kernel with nothing else on the GPU (in the timed region it overlaps other streams' kernels)
+    # the dominant kernel with nothing else on the GPU (inside the step it overlaps other streams' kernels)
     iso = []
+    wl.ck_t.set_profiling(True)
+    tbuf, tn = wl.ctx.device_buffer(0, wl.L._capi.FOLD_BUF_T)
     for _ in range(5):
-        for buf, nn in ((wl.W2[0], wl.nW), (wl.pipe.T, wl.nT)):
-            wl.ck.launch_device(buf.data_ptr(), nn, fmt=wl.L.FMT_MONTGOMERY, stream=0)
-            wl.ck.finish()
-            iso.append(wl.ck.last_profile()[0])
+        wl.ck_t.launch_device(tbuf, wl.nT, fmt=wl.L.FMT_MONTGOMERY, stream=0)
+        wl.ck_t.finish()
+        iso.append(wl.ck_t.last_profile()[0])
     iso = iso[2:]
 
-    iters = RC * world * args.steps
+    frames_total = RC * world if args.scaling == "weak" else RC
+    iters = frames_total * args.steps
     value = iters / (ms / 1e3)
     e2e = iters / (ms_e2e / 1e3)
-    out = None
     if rank == 0:
         peaks = {}
         try:
@@ -347,39 +502,35 @@ def run_gpu(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # dominant kernel: msm_accumulate_kernel; algorithmic bytes = 96 B per term
-        terms = (wl.nW + wl.nT) / 2.0
-        avg_ms = sum(acc_ms) / max(1, len(acc_ms))
         iso_ms = sum(iso) / max(1, len(iso))
+        terms = wl.nT
         achieved = terms * 96 / (iso_ms / 1e3) / 1e9 if iso_ms > 0 else 0.0
+        launches = st["launches_a"] + st["launches_b"] + st2["launches_a"] + st2["launches_b"]
         out = {
-            "metric": "Lurk iterations proved/sec (fib rc=100, Nova IVC)", "value": round(value, 2), "unit": "iterations/s",
+            "metric": METRIC, "value": round(value, 2), "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery integers)",
-            "data": "synthetic",
-            "config": {"workload": "fib rc=100 Nova IVC fold step on BN254/Grumpkin (benches/fibonacci.rs, configs[0]/metric config)",
-                       "composed": "per-fold GPU kernels: 2100 Poseidon slot witnesses + 300 bit-decomps, commit(W) 911900 terms, 6 SpMV + cross term "
-                                   "over 1114100 rows, commit(T), 2 AXPY, 2 secondary commits of 10^4; LEM synthesis / RO / reference Rust prover not included",
-                       "rc_per_gpu": RC, "commitment_key": "2^21 synthetic BN254 G1 points per GPU, contiguous shards"
-                                         + ("" if args.no_fixed_base else "; fixed-base window table (13 x 2^21 points) precomputed once, outside the timed region"),
-                       "l2": "inputs (128 MiB key + 64 MiB of vectors + 140 MiB CSR per step) exceed the 126 MB L2",
-                       "parallelism": f"frames/bases sharded over {world} GPU(s); all-gather of 2x96 B partial commitments"},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery integers)",
+            "data": "synthetic", "config": workload_config(world, args.scaling),
             "e2e": {"value": round(e2e, 2), "unit": "iterations/s", "h2d_bytes_per_step": int(wl.h2d_bytes),
                     "d2h_bytes_per_step": int(wl.d2h_bytes), "ms_per_step": round(ms_e2e / args.steps, 4)},
-            "gpu_launches": int(wl.launches * args.steps),
-            "roofline": {"kernel": "msm_accumulate_kernel (bucket accumulation of commit(W) / commit(T))", "bound": "hbm",
+            "gpu_launches": int(launches * args.steps),
+            "verified": verified,
+            "roofline": {"kernel": "msm_accumulate_kernel (bucket accumulation of commit(T) / commit(W))", "bound": "hbm",
                          "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
-                         "traffic": (1.92e9 if not args.no_fixed_base else 1.16e9),
-                         "traffic_note": "dram__bytes_read+write per launch from profiles/r1_ncu_full_msm_fixed_raw.csv (fixed-base) / "
-                                         "r1_ncu_full_msm_raw_final.csv; Pippenger gathers each 64-byte base once per window (13 x 64 B + index per term), "
-                                         "so traffic is ~19x the 96 B/term algorithmic figure by construction, still 10 % of DRAM bandwidth",
-                         "avg_launch_ms": round(iso_ms, 4), "avg_launch_ms_overlapped_in_step": round(avg_ms, 4), "algorithmic_bytes_per_launch": int(terms * 96),
+                         "traffic": ncu_traffic(),
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch in profiles/r2_ncu_full_msm_accumulate_raw.csv (ncu --set full of "
+                                         "this kernel at this size); Pippenger gathers each 64-byte window multiple once per window (13 x 64 B + index per term)",
+                         "avg_launch_ms": round(iso_ms, 4), "avg_launch_ms_overlapped_in_step": {"commit_W": round(st["accumulate_w_ms"], 4),
+                                                                                                "commit_T": round(st["accumulate_t_ms"], 4)},
+                         "algorithmic_bytes_per_launch": int(terms * 96),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                         "note": "bound by the FMA-heavy (IMAD.WIDE) pipe, 85-89 % busy in the ncu captures (profiles/): ~13 bucket "
-                                 "additions x ~1.4e3 IMAD.WIDE per 96 algorithmic bytes; launch time = CUDA events inside the library on "
-                                 "the launching stream, kernel run alone right after the timed region"},
+                         "note": "bound by the FMA-heavy (IMAD.WIDE) pipe (ncu captures in profiles/): ~13 bucket additions x ~1.4e3 IMAD.WIDE "
+                                 "per 96 algorithmic bytes; launch time = CUDA events inside the library on the launching stream, kernel run "
+                                 "alone right after the timed region"},
             "clocks": clocks,
         }
+        if args.latency_sms:
+            out["config"]["sm_partition"] = f"{args.latency_sms} SMs reserved for the latency-shaped kernels (green contexts)"
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sample_steps=1)
         print(json.dumps(out), flush=True)
@@ -389,65 +540,60 @@ def run_gpu(args):
 
 # ---------------------------------------------------------------------------------------------- CPU arm (oracle)
 class FoldStepCPU:
-    """the same composed step on the host cores through the oracle (plain C, OpenMP)"""
+    """the same fold on the host cores through the oracle (plain C + OpenMP for the vectors, Python for the few scalars)"""
 
-    def __init__(self, rc, seed=0x6c75726b):
-        from oracle import capi as oracle
-        self.o = oracle
-        self.threads = oracle.threads()
-        self.rc = rc
+    def __init__(self, frames, threads, seed=0x6c75726b):
+        from oracle import capi as oracle, nifs
+        self.o, self.nifs, self.th, self.frames = oracle, nifs, threads, frames
         rng = np.random.default_rng(seed)
-        self.nW, self.nT = rc * AUX_PER_FRAME, rc * CONS_PER_FRAME
+        mats, self.nW, self.nT, prod_rows = step_circuit(seed, frames)
         self.bases = oracle.gen_bases(CURVE, max(self.nW, self.nT))
-        self.bases2 = oracle.gen_bases(CURVE2, SECONDARY_N)
+        self.prim = nifs.NovaOracle(CURVE, self.bases, mats, self.nW, 2, nthreads=threads, pp_digest=PP_DIGEST)
+        mats2, self.nW2, self.nT2, _ = step_circuit(seed + 7, 1, slot_elems=SECONDARY_N - 1500, glue=1500, cons=SECONDARY_N)
+        self.sec = nifs.NovaOracle(CURVE2, oracle.gen_bases(CURVE2, max(self.nW2, self.nT2)), mats2, self.nW2, 2, nthreads=threads, pp_digest=PP_DIGEST)
         self.slot_pre = {}
         for arity, per_frame in SLOTS:
-            n = rc * per_frame
+            n = frames * per_frame
             pre = rand_elements(rng, n * arity).reshape(n, arity * 32)
             pre[rng.random(n) >= LIVE_SLOT_FRACTION] = 0
             self.slot_pre[arity] = pre.reshape(-1)
-            oracle.install_params(FIELD, arity)
-        self.bd = rand_elements(rng, rc * BITDECOMP_PER_FRAME, "witness")
-        self.slot_region = rc * 7808
+            oracle.install_params(0, arity)
+        self.bd = rand_elements(rng, frames * BITDECOMP_PER_FRAME, "witness")
+        self.offs = None
         self.W2 = rand_elements(rng, self.nW, "witness")
-        self.W1 = rand_elements(rng, self.nW)
-        self.E1 = rand_elements(rng, self.nT)
-        self.ncols = self.nW + 3
-        self.tail = rand_elements(rng, 3)
-        self.mats = [synthetic_r1cs(rng, self.nT, self.ncols, m) for m in (2.0, 2.0, 1.5)]
-        self.u1, self.u2 = rand_elements(rng, 1), rand_elements(rng, 1)
-        self.W_sec, self.T_sec = rand_elements(rng, SECONDARY_N, "witness"), rand_elements(rng, SECONDARY_N)
+        self.W2s = rand_elements(rng, self.nW2, "witness")
+        self.X2 = [3, 5]
+        self.prim.init_running(self.W2, self.X2)
+        self.sec.init_running(self.W2s, self.X2)
 
     def step(self):
-        o, th = self.o, self.threads
-        parts = [o.poseidon_witness_batch(FIELD, a, self.slot_pre[a], nthreads=th) for a, _ in SLOTS]
-        parts.append(o.bitdecomp_witness_batch(FIELD, self.bd, nthreads=th))
+        o, th = self.o, self.th
+        parts = [o.poseidon_witness_batch(0, a, self.slot_pre[a], nthreads=th) for a, _ in SLOTS]
+        parts.append(o.bitdecomp_witness_batch(0, self.bd, nthreads=th))
         slots = np.concatenate(parts)
-        self.W2[:slots.size] = slots
-        cw = o.msm(CURVE, self.bases, self.W2, nthreads=th)
-        z1 = np.concatenate([self.W1, self.tail])
-        z2 = np.concatenate([self.W2, self.tail])
-        mv = [o.spmv(FIELD, rp, col, val, z, nthreads=th) for (rp, col, val) in self.mats for z in (z1, z2)]
-        az1, az2, bz1, bz2, cz1, cz2 = mv
-        T = o.cross_term(FIELD, az1, bz1, cz1, az2, bz2, cz2, self.u1, self.u2, nthreads=th)
-        ct = o.msm(CURVE, self.bases, T, nthreads=th)
-        r = np.zeros(32, dtype=np.uint8)
-        r[:16] = np.frombuffer(hashlib.sha256(cw.tobytes() + ct.tobytes()).digest()[:16], dtype=np.uint8)
-        self.W1 = o.axpy(FIELD, self.W1, self.W2, r, nthreads=th)
-        self.E1 = o.axpy(FIELD, self.E1, T, r, nthreads=th)
-        o.msm(CURVE2, self.bases2, self.W_sec, nthreads=th)
-        o.msm(CURVE2, self.bases2, self.T_sec, nthreads=th)
+        self.W2[:slots.size] = slots             # same element count as the frame layout; positions do not change the work
+        self.prim.prove_step(self.W2, self.X2)
+        self.sec.prove_step(self.W2s, self.X2)
 
 
-def cpu_baseline(sample_steps=1, rc=RC):
+def host_threads():
+    """all the host threads the box has -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(sample_steps=1, frames=RC):
     """bounded sample of the same workload on the host cores (oracle = CPU port of the reference path)"""
-    wl = FoldStepCPU(rc)
+    th = host_threads()
+    wl = FoldStepCPU(frames, th)
     t0 = time.perf_counter()
     for _ in range(sample_steps):
         wl.step()
     dt = time.perf_counter() - t0
-    return {"value": round(rc * sample_steps / dt, 3), "unit": "iterations/s", "cores": wl.threads, "kind": "port",
-            "sample": f"{sample_steps} fold step(s) at rc={rc} ({dt:.1f} s): oracle/oracle.c, 4x64-bit Montgomery + OpenMP; "
+    return {"value": round(frames * sample_steps / dt, 3), "unit": "iterations/s", "cores": th, "kind": "port",
+            "sample": f"{sample_steps} fold step(s) of {frames} frames ({dt:.1f} s): oracle/oracle.c (4x64-bit Montgomery + OpenMP) + oracle/nifs.py; "
                       "the reference's Rust prover (hand-written asm MSM) cannot be built in this image"}
 
 
@@ -455,43 +601,37 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # size the per-step sample so that the whole run stays within a few minutes (~7 s per full-size step on 8 cores)
-    total = args.steps + args.warmup
-    rc = RC
-    est_full = 3.0 * (total + 2)
-    if est_full > 240.0:
-        rc = max(10, int(RC * 240.0 / est_full))
-    wl = FoldStepCPU(rc)
-    # all the host threads it can use: with SMT the oracle is sometimes faster on one thread per core -- time one
-    # warm-up step each way and keep the faster setting
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    th = host_threads()
+    wl = FoldStepCPU(RC, th)
+    # with SMT the oracle is sometimes faster on one thread per core -- time one warm-up step each way and keep the faster
     best = None
-    for th in sorted({wl.threads, max(1, wl.threads // 2)}, reverse=True):
-        wl.threads = th
+    for t in sorted({th, max(1, th // 2)}, reverse=True):
+        wl.th = wl.prim.th = wl.sec.th = t
         t0 = time.perf_counter()
         wl.step()
         dt1 = time.perf_counter() - t0
         if best is None or dt1 < best[0]:
-            best = (dt1, th)
-    wl.threads = best[1]
-    for _ in range(max(0, args.warmup - 2)):
+            best = (dt1, t)
+    wl.th = wl.prim.th = wl.sec.th = best[1]
+    # bounded: the whole run stays within a few minutes whatever --steps says (each step is ~2 s on 64 cores, ~8 s on 8)
+    budget_s = 150.0
+    steps = max(1, min(args.steps, int(budget_s / max(best[0], 1e-3))))
+    for _ in range(max(0, min(args.warmup, 3) - 2)):
         wl.step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         wl.step()
     dt = time.perf_counter() - t0
-    value = rc * args.steps / dt
-    sample = (f"each step = one fold at rc={rc} (of the rc={RC} workload), all {wl.threads} host threads, oracle/oracle.c "
-              "(CPU port; upstream Rust prover not buildable here)")
+    value = RC * steps / dt
+    sample = (f"{steps} timed fold step(s) of {RC} frames each (one rank's share of the workload; per-frame cost does not depend on the frame count), "
+              f"{wl.th} host threads, oracle/oracle.c + oracle/nifs.py (CPU port; upstream Rust prover not buildable here)")
     print(json.dumps({
-        "impl": "reference", "metric": "Lurk iterations proved/sec (fib rc=100, Nova IVC)", "value": round(value, 3),
-        "unit": "iterations/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64x4 (254-bit Montgomery integers)", "data": "synthetic",
-        "config": {"workload": "fib rc=100 Nova IVC fold step on BN254/Grumpkin (benches/fibonacci.rs, configs[0]/metric config)",
-                   "composed": "the same per-fold work as the B200 arm (2100 Poseidon slot witnesses + 300 bit-decomps, commit(W), 6 SpMV + cross term, "
-                               "commit(T), 2 AXPY, 2 secondary commits) on the host cores through oracle/oracle.c",
-                   "rc_sample": rc},
-        "cpu_baseline": {"value": round(value, 3), "unit": "iterations/s", "cores": wl.threads, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": round(value, 3),
+        "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "u64x4 (254-bit Montgomery integers)", "data": "synthetic", "config": workload_config(world, args.scaling),
+        "cpu_baseline": {"value": round(value, 3), "unit": "iterations/s", "cores": wl.th, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -502,8 +642,10 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = rc 100 per GPU (rc = 100 N step circuit); strong = ONE rc = 100 fold, its key split N ways")
+    ap.add_argument("--latency-sms", type=int, default=0, help="SM partition (green contexts): SMs reserved for the chain's latency-shaped kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fixed-base", action="store_true", help="do not precompute window multiples of the commitment key")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -50,10 +50,13 @@ struct MsmPlan {
 };
 static constexpr uint32_t MSM_MAX_RESULT_POINTS = 512;    // rwin * nq <= 64 * 1 .. 13 * 17: read back per commitment
 
+// Window width of the fixed-base mode: 2^(c-1) buckets for ~n * 254 / c entries.  c = 20 from half a million bases up (the
+// step circuit's witness, 911 900 terms, and a 2^21-point key get the same 13 windows); smaller keys keep >= 20 entries per
+// bucket so that the bucket reduction (2 additions per bucket) stays a small fraction of the accumulation.
 inline int fixed_base_window(size_t key_n) {
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= key_n) lg++;
-    return std::min(20, std::max(10, lg - 1));
+    return std::min(20, std::max(10, lg + 1));
 }
 
 inline MsmPlan make_plan(size_t n, int scalar_bits, int fixed_c = 0) {
