@@ -72,55 +72,71 @@ def small_vals(rng, n):
     return val.reshape(-1)
 
 
-def step_circuit(seed, frames, slot_elems=SLOT_ELEMS, glue=GLUE_PER_FRAME, cons=CONS_PER_FRAME, n_x=2):
-    """Synthetic R1CS in the shape of the Lurk step circuit, satisfiable by construction (same rule as
-    oracle/nifs.py:synthetic_step_circuit, vectorised): per frame `glue` product rows (a . slots)(b . slots) = glue_g and
-    cons - glue linear rows (a . z) u = (a . z).  Columns: frame-major W, then u, then X.  Values canonical small ints.
-    Returns [(row_ptr, col, val)] x 3, n_w, rows, product_rows (global row index of every product row, frame-major)."""
+def step_circuit(seed, frames, slot_elems=SLOT_ELEMS, glue=GLUE_PER_FRAME, cons=CONS_PER_FRAME, n_x=2, linear_fraction=0.02):
+    """Synthetic R1CS in the shape of the Lurk step circuit, satisfiable by construction AND with a dense cross term (as the
+    real circuit's: every constraint is a genuine product).  Per frame: `glue` defining rows (a_k . slots)(b_k . slots) = glue_k
+    -- the LEM-body aux stand-in -- and cons - glue further rows that re-state a definition k = row mod glue with other
+    coefficients, (l a_k . slots)(m b_k . slots) = l m glue_k, except a small fraction of linear rows (a . z) u = (a . z) that
+    also touch the public IO (their cross term vanishes identically).  Columns: frame-major W, then u, then X.  Values are
+    canonical small integers.  Returns [(row_ptr, col, val)] x 3, n_w, rows, the global row index of every defining row."""
     rng = np.random.default_rng(seed)
     per = slot_elems + glue
     n_w, rows = frames * per, frames * cons
-    lin = cons - glue
-    frame_of_row = np.repeat(np.arange(frames, dtype=np.int64), cons)
-    local = np.tile(np.arange(cons, dtype=np.int64), frames)
-    is_prod = local < glue
+    # ---- the definitions of one frame layout (shared by all frames up to the column base)
+    na = rng.integers(1, 4, size=glue)                       # non-zeros of a_k: 1..3
+    nb = rng.integers(1, 3, size=glue)                       # non-zeros of b_k: 1..2
+    a_ptr = np.concatenate([[0], np.cumsum(na)])
+    b_ptr = np.concatenate([[0], np.cumsum(nb)])
+    a_col = rng.integers(0, slot_elems, size=int(a_ptr[-1]))
+    b_col = rng.integers(0, slot_elems, size=int(b_ptr[-1]))
+    a_cf = rng.integers(1, 4, size=int(a_ptr[-1]))
+    b_cf = rng.integers(1, 4, size=int(b_ptr[-1]))
+    # ---- rows of one frame
+    local = np.arange(cons)
+    k = local % glue
+    is_lin = (local >= glue) & (rng.random(cons) < linear_fraction)
+    lam = np.where(local < glue, 1, rng.integers(1, 3, size=cons))
+    mu = np.where(local < glue, 1, rng.integers(1, 3, size=cons))
 
-    def random_rows(nnz_hi_prod, nnz_hi_lin):
-        nnz = np.where(is_prod, rng.integers(1, nnz_hi_prod + 1, size=rows), rng.integers(1, nnz_hi_lin + 1, size=rows))
-        rp = np.concatenate([[0], np.cumsum(nnz)]).astype(np.uint64)
-        r_of = np.repeat(np.arange(rows), nnz)
-        span = np.where(is_prod[r_of], slot_elems, per)
-        col = frame_of_row[r_of] * per + (rng.random(r_of.size) * span).astype(np.int64)
-        return rp, col.astype(np.uint32), small_vals(rng, r_of.size)
+    def expand(ptr, col, cf, scale, lin_cols, lin_cf):
+        """per-frame CSR of rows taking definition k's entries scaled, or the linear row's own entries"""
+        cnt = np.where(is_lin, lin_cols.shape[1], ptr[k + 1] - ptr[k])
+        rp = np.concatenate([[0], np.cumsum(cnt)])
+        cols = np.empty(int(rp[-1]), dtype=np.int64)
+        vals = np.empty(int(rp[-1]), dtype=np.int64)
+        r_of = np.repeat(local, cnt)
+        within = np.arange(int(rp[-1])) - rp[r_of]
+        d = ~is_lin[r_of]
+        src = ptr[k[r_of[d]]] + within[d]
+        cols[d] = col[src]
+        vals[d] = cf[src] * scale[r_of[d]]
+        cols[~d] = lin_cols[r_of[~d], within[~d]]
+        vals[~d] = lin_cf[r_of[~d], within[~d]]
+        return rp, cols, vals
 
-    A = random_rows(3, 3)
-    # B: product rows as A (1..2 slot columns); linear rows = the u column with coefficient 1
-    nnz = np.where(is_prod, rng.integers(1, 3, size=rows), 1)
-    rp = np.concatenate([[0], np.cumsum(nnz)]).astype(np.uint64)
-    r_of = np.repeat(np.arange(rows), nnz)
-    col = np.where(is_prod[r_of], frame_of_row[r_of] * per + (rng.random(r_of.size) * slot_elems).astype(np.int64), n_w)
-    val = small_vals(rng, r_of.size).reshape(-1, 32)
-    val[~is_prod[r_of]] = 0
-    val[~is_prod[r_of], 0] = 1
-    B = (rp, col.astype(np.uint32), val.reshape(-1))
-    # C: product rows = the glue column they define; linear rows = their A row
-    a_rp, a_col, a_val = A
-    a_nnz = np.diff(a_rp.astype(np.int64))
-    c_nnz = np.where(is_prod, 1, a_nnz)
-    c_rp = np.concatenate([[0], np.cumsum(c_nnz)]).astype(np.uint64)
-    c_col = np.empty(int(c_rp[-1]), dtype=np.uint32)
-    c_val = np.zeros((int(c_rp[-1]), 32), dtype=np.uint8)
-    a_r_of = np.repeat(np.arange(rows), a_nnz)
-    keep = ~is_prod[a_r_of]
-    c_r_of = np.repeat(np.arange(rows), c_nnz)
-    lin_mask = ~is_prod[c_r_of]
-    c_col[lin_mask] = a_col[keep]
-    c_val[lin_mask] = a_val.reshape(-1, 32)[keep]
-    prod_rows = np.nonzero(is_prod)[0]
-    c_col[~lin_mask] = (frame_of_row[prod_rows] * per + slot_elems + local[prod_rows]).astype(np.uint32)
-    c_val[~lin_mask, 0] = 1
-    C = (c_rp, c_col, c_val.reshape(-1))
-    return [A, B, C], n_w, rows, prod_rows
+    # linear rows: two W columns of the frame + one public-IO column (marked -1 - j, resolved below), coefficient 1..3
+    lin_cols = np.stack([rng.integers(0, per, size=cons), rng.integers(0, per, size=cons), -1 - rng.integers(0, n_x, size=cons)], axis=1)
+    lin_cf = rng.integers(1, 4, size=(cons, 3))
+    U = -100                                                   # marker of the u column
+    fa = expand(a_ptr, a_col, a_cf, lam, lin_cols, lin_cf)
+    fb = expand(b_ptr, b_col, b_cf, mu, np.full((cons, 1), U), np.ones((cons, 1), dtype=np.int64))
+    # C: defining / restating rows -> lam * mu at the glue column; linear rows -> their A row
+    c_ptr = np.arange(glue + 1)
+    fc = expand(c_ptr, slot_elems + np.arange(glue), np.ones(glue, dtype=np.int64), lam * mu, lin_cols, lin_cf)
+
+    def tile(frame_csr):
+        rp, cols, vals = frame_csr
+        nnz = int(rp[-1])
+        all_rp = (np.arange(frames, dtype=np.int64)[:, None] * nnz + rp[None, :-1]).reshape(-1)
+        all_rp = np.concatenate([all_rp, [frames * nnz]]).astype(np.uint64)
+        base = np.arange(frames, dtype=np.int64)[:, None] * per
+        c = np.where(cols[None, :] >= 0, base + cols[None, :], np.where(cols[None, :] == U, n_w, n_w + 1 + (-1 - cols[None, :])))
+        v = np.zeros((frames * nnz, 32), dtype=np.uint8)
+        v[:, 0] = np.tile(vals, frames).astype(np.uint8)
+        return all_rp, c.reshape(-1).astype(np.uint32), v.reshape(-1)
+
+    prod_rows = (np.arange(frames, dtype=np.int64)[:, None] * cons + np.arange(glue)[None, :]).reshape(-1)
+    return [tile(fa), tile(fb), tile(fc)], n_w, rows, prod_rows
 
 
 def slot_offsets(frames):

@@ -113,7 +113,8 @@ class NovaOracle:
 def synthetic_step_circuit(rng, frames, slot_elems, glue, lin_rows, n_x=2):
     """Satisfiable-by-construction R1CS in the shape of a Lurk step circuit: per frame `slot_elems` slot-witness columns
     (any values), `glue` columns each DEFINED as (a . slots) * (b . slots) of the same frame -- the LEM body aux stand-in
-    -- and `lin_rows` linear rows (a . z) * u = (a . z) that hold for every z.  Columns: frame-major W, then u, then X.
+    --, the same `glue` definitions restated with other coefficients, and `lin_rows` linear rows (a . z) * u = (a . z)
+    that hold for every z (their cross term vanishes).  Columns: frame-major W, then u, then X.
     Returns (mats, n_w, glue_fn) where glue_fn(W2 bytes with slot columns filled, p) -> glue values per frame."""
     per = slot_elems + glue
     n_w = frames * per
@@ -128,6 +129,12 @@ def synthetic_step_circuit(rng, frames, slot_elems, glue, lin_rows, n_x=2):
             b = [(base + int(c), small()) for c in rng.choice(slot_elems, size=int(rng.integers(1, 3)), replace=False)]
             A.append(a); B.append(b); Cm.append([(base + slot_elems + g, 1)])
             defs.append((base + slot_elems + g, a, b))
+        for g in range(glue):
+            # the same definition restated with other coefficients: (l a . s)(m b . s) = l m glue_g -- keeps the system
+            # satisfiable while most rows have a non-vanishing cross term, as in a real circuit
+            dst, a, b = defs[len(defs) - glue + g]
+            l, m = small(), small()
+            A.append([(c, v * l) for c, v in a]); B.append([(c, v * m) for c, v in b]); Cm.append([(dst, l * m)])
         for _ in range(lin_rows):
             cols = [base + int(c) for c in rng.choice(per, size=int(rng.integers(1, 4)), replace=False)]
             if rng.random() < 0.3:

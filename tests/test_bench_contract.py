@@ -62,5 +62,6 @@ def test_synthetic_step_circuit_is_satisfiable_by_construction():
         W[f * per + slot_elems + g] = az[row] * bz[row] % p
     o = nifs.NovaOracle(0, capi.gen_bases(0, max(n_w, rows)), mats, n_w, 2)
     assert o.bad_rows(nifs.pack(W), np.zeros(rows * 32, dtype=np.uint8), 1, X) == 0
-    W[0] = (W[0] + 1) % p
+    c = int(mats[0][1][0])                                   # a slot column that the first defining row reads
+    W[c] = (W[c] + 1) % p
     assert o.bad_rows(nifs.pack(W), np.zeros(rows * 32, dtype=np.uint8), 1, X) > 0
