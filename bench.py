@@ -261,31 +261,27 @@ class FoldStepGPU:
         common = np.random.default_rng(seed + 99)
         self.X2 = [int(common.integers(1, 2**62)) * int(common.integers(1, 2**62)) for _ in range(2)]
         self.X2s = [int(common.integers(1, 2**62)) * int(common.integers(1, 2**62)) for _ in range(2)]
-        pre = {}
-        for arity, idx in self.batch:
-            n = self.frames * (dict(SLOTS).get(arity, BITDECOMP_PER_FRAME))
-            if arity:
-                x = rand_elements(rng, n * arity).reshape(n, arity * 32)
-                x[rng.random(n) >= LIVE_SLOT_FRACTION] = 0
-                pre[idx] = x.reshape(-1)
-            else:
-                pre[idx] = rand_elements(rng, n, "witness")
-        ro = self._ro_consts(self.X2, P_FQ)
         # every input is handed over in Montgomery form (the in-memory form of halo2curves' field types); the random bytes
-        # below are < p, i.e. valid Montgomery representatives of uniformly random elements
+        # below are < p, i.e. valid Montgomery representatives of uniformly random elements.  The two fresh-instance buffers
+        # get DIFFERENT inputs: folding the same instance over and over would make every cross term vanish identically.
+        ro = self._ro_consts(self.X2, P_FQ)
         for b in range(2):
-            for idx, x in pre.items():
-                self.ctx.host_buffer(b, idx)[:] = x
+            for arity, idx in self.batch:
+                n = self.frames * (dict(SLOTS).get(arity, BITDECOMP_PER_FRAME))
+                if arity:
+                    x = rand_elements(rng, n * arity).reshape(n, arity * 32)
+                    x[rng.random(n) >= LIVE_SLOT_FRACTION] = 0
+                    self.ctx.host_buffer(b, idx)[:] = x.reshape(-1)
+                else:
+                    self.ctx.host_buffer(b, idx)[:] = rand_elements(rng, n, "witness")
             self.ctx.host_buffer(b, L._capi.FOLD_BUF_X2)[:] = to_mont(self._pack(self.X2), P_FR)
             self.ctx.host_buffer(b, L._capi.FOLD_BUF_RO)[:] = ro
-        # run the slot kernels once to learn the slot columns, then define the LEM-body aux from them (product rows)
-        self._derive_glue(self.ctx, self.mats, self.prod_rows, self.nW, self.nT, P_FR, slots=True)
-        w2 = to_mont(rand_elements(rng, self.nW2, "witness"), P_FQ)
-        for b in range(2):
-            self.ctx2.host_buffer(b, L._capi.FOLD_BUF_GLUE)[:] = w2
+            # run the slot kernels once to learn the slot columns, then define the LEM-body aux from them (defining rows)
+            self._derive_glue(self.ctx, b, self.mats, self.prod_rows, self.nW, self.nT, P_FR, slots=True)
+            self.ctx2.host_buffer(b, L._capi.FOLD_BUF_GLUE)[:] = to_mont(rand_elements(rng, self.nW2, "witness"), P_FQ)
             self.ctx2.host_buffer(b, L._capi.FOLD_BUF_X2)[:] = to_mont(self._pack(self.X2s), P_FQ)
             self.ctx2.host_buffer(b, L._capi.FOLD_BUF_RO)[:] = self._ro_consts(self.X2s, P_FR)
-        self._derive_glue(self.ctx2, self.mats2, self.prod2, self.nW2, self.nT2, P_FQ, slots=False)
+            self._derive_glue(self.ctx2, b, self.mats2, self.prod2, self.nW2, self.nT2, P_FQ, slots=False)
         self.h2d_bytes = sum(self.ctx.host_buffer(0, w).size for w in [i for _, i in self.batch] + [-1, -2, -3]) + \
             sum(self.ctx2.host_buffer(0, w).size for w in (-1, -2, -3))
         self.d2h_bytes = 2 * 448                         # the two result records
@@ -303,16 +299,16 @@ class FoldStepGPU:
             ro[pos] = self._pack([v])
         return to_mont(ro.reshape(-1), p_base)
 
-    def _derive_glue(self, ctx, mats, prod_rows, n_w, n_rows, p, slots):
+    def _derive_glue(self, ctx, b, mats, prod_rows, n_w, n_rows, p, slots):
         """setup: make the fresh instance satisfy the circuit -- glue_g = (A_g . z)(B_g . z) for the product rows, computed with
         the library's own SpMV / cross-term kernels on the device from the slot columns the slot kernels produce"""
         t, L = self.torch, self.L
         lib = L._capi.lib()
         M = L.FMT_MONTGOMERY
         field = 0 if p == P_FR else 1
-        ctx.stage_a(0, fmt=M)          # with the glue still zero: fills the slot columns of W2 / uploads the dense witness
+        ctx.stage_a(b, fmt=M)          # with the glue still zero: fills the slot columns of W2 / uploads the dense witness
         ctx.sync()
-        z2 = ctx.device_view(0, L._capi.FOLD_BUF_W2)
+        z2 = ctx.device_view(b, L._capi.FOLD_BUF_W2)
         dev = lambda a: t.from_numpy(np.ascontiguousarray(a)).cuda()
         out = []
         for rp, col, val in mats[:2]:
@@ -328,14 +324,10 @@ class FoldStepGPU:
         t.cuda.synchronize()
         glue = prod.view(n_rows, 32)[dev(prod_rows.astype(np.int64))].cpu().numpy().reshape(-1)
         if slots:
-            for b in range(2):
-                ctx.host_buffer(b, L._capi.FOLD_BUF_GLUE)[:] = glue
+            ctx.host_buffer(b, L._capi.FOLD_BUF_GLUE)[:] = glue
         else:
             # secondary: the glue columns are the tail of the dense witness
-            per = n_w
-            g = glue.size // 32
-            for b in range(2):
-                ctx.host_buffer(b, L._capi.FOLD_BUF_GLUE)[(per - g) * 32:] = glue
+            ctx.host_buffer(b, L._capi.FOLD_BUF_GLUE)[(n_w - glue.size // 32) * 32:] = glue
         del z2
 
     # ------------------------------------------------------------------------------------------ the step loop
