@@ -170,7 +170,7 @@ def workload_config(world, scaling):
                         "per 100 frames; commit(W) 911900 terms; 6 SpMV + cross term over 1114100 rows; commit(T); Poseidon-sponge RO challenge; "
                         "fold of (W,u,X), E and both commitments; the same fold of a 10^4-constraint secondary circuit on Grumpkin. "
                         "LEM synthesis / augmented-circuit synthesis / reference Rust prover not included",
-            "frames_per_step": frames, "scaling": scaling,
+            "frames_per_step": frames, "scaling": scaling, "live_slot_fraction": LIVE_SLOT_FRACTION,
             "commitment_key": "2^21 synthetic BN254 G1 points per 100 frames ([i+1]G), sharded by frame; fixed-base window tables built once",
             "l2": "inputs per step (128 MiB key, 1.7 GB window table, 64 MiB of vectors, 140 MiB CSR) exceed the 126 MB L2",
             "parallelism": f"frames/bases sharded over {world} GPU(s); partial commitments exchanged through NVLink peer memory inside the challenge kernel"}
@@ -645,6 +645,7 @@ def run_reference(args):
 
 
 def main():
+    global LIVE_SLOT_FRACTION
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -653,8 +654,11 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = rc 100 per GPU (rc = 100 N step circuit); strong = ONE rc = 100 fold, its key split N ways")
     ap.add_argument("--latency-sms", type=int, default=0, help="SM partition (green contexts): SMs reserved for the chain's latency-shaped kernels")
+    ap.add_argument("--live-slots", type=float, default=LIVE_SLOT_FRACTION,
+                    help="fraction of a frame's slots with a non-dummy preimage (dummy slots share one witness, multiframe.rs:553-577)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    LIVE_SLOT_FRACTION = args.live_slots
     if args.impl == "reference":
         run_reference(args)
     else:

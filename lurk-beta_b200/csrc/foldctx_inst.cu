@@ -47,7 +47,7 @@ struct FoldCtx final : FoldCtxBase {
     size_t nz = 0;                          // |z| = n_w + 1 + n_x
     int D = 2;
     lurk_msm_ctx *ckW[FOLD_MAX_DEPTH] = {nullptr, nullptr, nullptr, nullptr};
-    lurk_msm_ctx *ckT = nullptr, *ckChk = nullptr;
+    lurk_msm_ctx *ckT = nullptr, *ckChk = nullptr, *ckChkW = nullptr;
     DevBuf z1, e1, T, mv1[3], z2[FOLD_MAX_DEPTH], mv2[FOLD_MAX_DEPTH][3];
     DevBuf csr_rp[3], csr_col[3], csr_val[3];
     CsrDev csr[3];
@@ -69,7 +69,8 @@ struct FoldCtx final : FoldCtxBase {
     bool peers_open[FOLD_MAX_WORLD];
     bool peers_set = false;
     // streams / events
-    cudaStream_t sH = nullptr, sK[3] = {nullptr, nullptr, nullptr}, sA = nullptr, sB = nullptr, sC = nullptr, sAcc = nullptr;
+    cudaStream_t sH = nullptr, sK[3] = {nullptr, nullptr, nullptr}, sA = nullptr, sB = nullptr, sC = nullptr, sT = nullptr;
+    bool partitioned = false;
     cudaEvent_t ev_h2d[FOLD_MAX_DEPTH], ev_slot[FOLD_MAX_DEPTH][3], ev_cw[FOLD_MAX_DEPTH], ev_A[FOLD_MAX_DEPTH], ev_fold[FOLD_MAX_DEPTH],
         ev_chal[FOLD_MAX_DEPTH + 1], ev_done[FOLD_MAX_DEPTH + 1];
     bool fold_recorded[FOLD_MAX_DEPTH] = {false, false, false, false};
@@ -111,10 +112,11 @@ struct FoldCtx final : FoldCtxBase {
         }
         if (ckT) lurk_msm_ctx_destroy(ckT);
         if (ckChk) lurk_msm_ctx_destroy(ckChk);
+        if (ckChkW) lurk_msm_ctx_destroy(ckChkW);
         for (auto &sb : batches)
             for (int b = 0; b < FOLD_MAX_DEPTH; b++)
                 if (sb->h_pre[b]) cudaFreeHost(sb->h_pre[b]);
-        for (cudaStream_t s : {sH, sK[0], sK[1], sK[2], sA, sB, sC, sAcc})
+        for (cudaStream_t s : {sH, sK[0], sK[1], sK[2], sA, sB, sC, partitioned ? sT : (cudaStream_t) nullptr})
             if (s) cudaStreamDestroy(s);
         green_destroy();
     }
@@ -141,8 +143,9 @@ struct FoldCtx final : FoldCtxBase {
                 if (g) fn((CUgreenCtx)g);
         green[0] = green[1] = nullptr;
     }
-    // returns LURK_OK and leaves the streams null when partitioning is unavailable (the caller falls back to plain streams)
-    int green_streams(int latency_sms, cudaStream_t *lat, cudaStream_t *thr_hi, cudaStream_t *thr_lo, int n_lo) {
+    // Splits the device into a tiny partition (`tiny_sms` SMs: the single-CTA kernels of the chain) and the rest (everything
+    // else) and creates the streams of both.
+    int green_streams(int tiny_sms, cudaStream_t *tiny, int n_tiny, cudaStream_t *big_hi, cudaStream_t *big_lo, int n_lo) {
         typedef CUresult (*get_res_t)(CUdevice, CUdevResource *, CUdevResourceType);
         typedef CUresult (*split_t)(CUdevResource *, unsigned *, const CUdevResource *, CUdevResource *, unsigned, unsigned);
         typedef CUresult (*gen_desc_t)(CUdevResourceDesc *, CUdevResource *, unsigned);
@@ -156,16 +159,17 @@ struct FoldCtx final : FoldCtxBase {
         CUdevResource all, part, rest;
         if (get_res((CUdevice)device, &all, CU_DEV_RESOURCE_TYPE_SM)) return LURK_ERR_CUDA;
         unsigned groups = 1;
-        if (split(&part, &groups, &all, &rest, 0, (unsigned)latency_sms) || groups != 1) return LURK_ERR_CUDA;
+        if (split(&part, &groups, &all, &rest, 0, (unsigned)tiny_sms) || groups != 1) return LURK_ERR_CUDA;
         CUdevResourceDesc desc[2] = {nullptr, nullptr};
         if (gen_desc(&desc[0], &part, 1) || gen_desc(&desc[1], &rest, 1)) return LURK_ERR_CUDA;
         if (green_create((CUgreenCtx *)&green[0], desc[0], (CUdevice)device, CU_GREEN_CTX_DEFAULT_STREAM) ||
             green_create((CUgreenCtx *)&green[1], desc[1], (CUdevice)device, CU_GREEN_CTX_DEFAULT_STREAM)) { green_destroy(); return LURK_ERR_CUDA; }
         partition_sms[0] = (int)part.sm.smCount;
         partition_sms[1] = (int)rest.sm.smCount;
-        int rc = green_stream((CUstream *)lat, (CUgreenCtx)green[0], CU_STREAM_NON_BLOCKING, -1);
-        rc |= green_stream((CUstream *)thr_hi, (CUgreenCtx)green[1], CU_STREAM_NON_BLOCKING, -1);
-        for (int k = 0; k < n_lo; k++) rc |= green_stream((CUstream *)(thr_lo + k), (CUgreenCtx)green[1], CU_STREAM_NON_BLOCKING, 0);
+        int rc = 0;
+        for (int k = 0; k < n_tiny; k++) rc |= green_stream((CUstream *)(tiny + k), (CUgreenCtx)green[0], CU_STREAM_NON_BLOCKING, -1);
+        rc |= green_stream((CUstream *)big_hi, (CUgreenCtx)green[1], CU_STREAM_NON_BLOCKING, -1);
+        for (int k = 0; k < n_lo; k++) rc |= green_stream((CUstream *)(big_lo + k), (CUgreenCtx)green[1], CU_STREAM_NON_BLOCKING, 0);
         if (rc) { green_destroy(); return LURK_ERR_CUDA; }
         return LURK_OK;
     }
@@ -187,37 +191,34 @@ struct FoldCtx final : FoldCtxBase {
         for (int b = 0; b < D; b++) LURK_TRY(lurk_msm_ctx_clone(ck_w, &ckW[b]));
         LURK_TRY(lurk_msm_ctx_clone(ck_t, &ckT));
         LURK_TRY(lurk_msm_ctx_clone(ck_t, &ckChk));
+        LURK_TRY(lurk_msm_ctx_clone(ck_w, &ckChkW));     // check_running must not touch a prefetched commit(W2)
         for (int b = 0; b < D; b++) lurk_msm_ctx_set_profiling(ckW[b], 1);
         lurk_msm_ctx_set_profiling(ckT, 1);
 
         // streams: the chain gets the high priority; optional SM partition
         int lo = 0, hi = 0;
         LURK_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        bool partitioned = false;
         if (c.latency_sms > 0) {
-            cudaStream_t thr_lo[4] = {nullptr, nullptr, nullptr, nullptr};
-            if (green_streams(c.latency_sms, &sB, &sAcc, thr_lo, 4) == LURK_OK) {
-                sK[0] = thr_lo[0]; sK[1] = thr_lo[1]; sK[2] = thr_lo[2]; sA = thr_lo[3];
-                partitioned = true;
-            } else {
+            cudaStream_t tiny[2] = {nullptr, nullptr}, big_lo[4] = {nullptr, nullptr, nullptr, nullptr};
+            if (green_streams(c.latency_sms, tiny, 2, &sB, big_lo, 4) != LURK_OK) {
                 set_error("SM partitioning (green contexts) is not available on this driver");
                 return LURK_ERR_CUDA;
             }
-        }
-        if (!partitioned) {
+            sT = tiny[0]; sC = tiny[1];
+            sK[0] = big_lo[0]; sK[1] = big_lo[1]; sK[2] = big_lo[2]; sA = big_lo[3];
+            partitioned = true;
+        } else {
             LURK_CUDA_TRY(cudaStreamCreateWithPriority(&sB, cudaStreamNonBlocking, hi));
             for (int k = 0; k < 3; k++) LURK_CUDA_TRY(cudaStreamCreateWithPriority(&sK[k], cudaStreamNonBlocking, lo));
             LURK_CUDA_TRY(cudaStreamCreateWithPriority(&sA, cudaStreamNonBlocking, lo));
+            LURK_CUDA_TRY(cudaStreamCreateWithPriority(&sC, cudaStreamNonBlocking, lo));
+            sT = sB;                       // no partition: the single-CTA kernels stay on the chain's stream
         }
         LURK_CUDA_TRY(cudaStreamCreateWithPriority(&sH, cudaStreamNonBlocking, lo));
-        LURK_CUDA_TRY(cudaStreamCreateWithPriority(&sC, cudaStreamNonBlocking, lo));
         if (partitioned) {
-            // accumulate kernels of every commitment go to the throughput partition; commit(W)'s latency-shaped part shares
-            // the latency partition with the chain (lower priority stream of the same green context is not available
-            // through this API, so it simply queues behind)
-            for (lurk_msm_ctx *m : {ckW[0], ckW[1], ckW[2], ckW[3], ckT}) {
+            for (lurk_msm_ctx *m : {ckW[0], ckW[1], ckW[2], ckW[3], ckT, ckChk, ckChkW}) {
                 if (!m) continue;
-                m->acc_stream = sAcc;
+                m->tiny_stream = sT;
                 LURK_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
                 LURK_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
             }
@@ -549,7 +550,7 @@ struct FoldCtx final : FoldCtxBase {
         // comm_W2 (this rank's share): result stays on the device for the challenge kernel
         LURK_TRY(msm_launch<C>(ckW[b], W2, cfg.n_w, LURK_FMT_MONTGOMERY, sK[0], false));
         k += ckW[b]->last_launches;
-        LURK_CUDA_TRY(cudaEventRecord(ev_cw[b], sK[0]));
+        LURK_CUDA_TRY(cudaEventRecord(ev_cw[b], partitioned ? sT : sK[0]));   // where msm_horner_kernel ran
         // A z2, B z2, C z2
         for (int s = 0; s < 3; s++) LURK_CUDA_TRY(cudaStreamWaitEvent(sA, ev_slot[b][s], 0));
         if (cfg.n_rows) {
@@ -602,14 +603,15 @@ struct FoldCtx final : FoldCtxBase {
         if (!a_recorded[b]) { set_error("buffer %d: stage A has not been enqueued", b); return LURK_ERR_ARG; }
         if (b_pending[b]) { set_error("buffer %d: result not collected", b); return LURK_ERR_ARG; }
         LURK_CUDA_TRY(cudaStreamWaitEvent(sB, ev_A[b], 0));
-        LURK_CUDA_TRY(cudaStreamWaitEvent(sB, ev_cw[b], 0));
         LURK_CUDA_TRY(cudaMemcpyAsync(z1.p, z2[b].p, nz * sizeof(Fs), cudaMemcpyDeviceToDevice, sB));
         LURK_CUDA_TRY(cudaMemsetAsync(e1.p, 0, (size_t)cfg.n_rows * sizeof(Fs), sB));
-        fold_challenge_kernel<C><<<1, 64, 0, sB>>>(challenge_args(ckW[b]->scratch.result.template as<Pt>(), nullptr, b, b, FOLD_MODE_COMMIT_ONLY));
+        LURK_CUDA_TRY(cudaStreamWaitEvent(sT, ev_cw[b], 0));
+        fold_challenge_kernel<C><<<1, 64, 0, sT>>>(challenge_args(ckW[b]->scratch.result.template as<Pt>(), nullptr, b, b, FOLD_MODE_COMMIT_ONLY));
         LURK_CUDA_TRY(cudaGetLastError());
-        LURK_CUDA_TRY(cudaEventRecord(ev_fold[b], sB));
+        LURK_CUDA_TRY(cudaEventRecord(ev_chal[b], sT));
+        if (sT != sB) LURK_CUDA_TRY(cudaStreamWaitEvent(sB, ev_chal[b], 0));
+        LURK_CUDA_TRY(cudaEventRecord(ev_fold[b], sB));     // after the last reader of W2[b] and of commit(W2[b])'s result
         fold_recorded[b] = true;
-        LURK_CUDA_TRY(cudaEventRecord(ev_chal[b], sB));
         LURK_CUDA_TRY(cudaStreamWaitEvent(sC, ev_chal[b], 0));
         fold_commitments_kernel<C><<<1, 64, 0, sC>>>(run_pts.as<Pt>(), run_pts.as<Pt>() + 1, rec_dev[b].as<Rec>(), 1);
         LURK_CUDA_TRY(cudaGetLastError());
@@ -644,11 +646,17 @@ struct FoldCtx final : FoldCtxBase {
         }
         LURK_TRY(msm_launch<C>(ckT, T.p, rows, LURK_FMT_MONTGOMERY, sB, false));
         k += rows ? ckT->last_launches : 0;
-        LURK_CUDA_TRY(cudaStreamWaitEvent(sB, ev_cw[b], 0));
-        fold_challenge_kernel<C><<<1, 64, 0, sB>>>(challenge_args(ckW[b]->scratch.result.template as<Pt>(), ckT->scratch.result.template as<Pt>(), b, b,
+        // the finished partial commitments are on sT (the tiny partition's stream, or sB itself without a partition)
+        if (sT != sB && !rows) {           // an empty T is produced by a memset on sB
+            LURK_CUDA_TRY(cudaEventRecord(ev_chal[b], sB));
+            LURK_CUDA_TRY(cudaStreamWaitEvent(sT, ev_chal[b], 0));
+        }
+        LURK_CUDA_TRY(cudaStreamWaitEvent(sT, ev_cw[b], 0));
+        fold_challenge_kernel<C><<<1, 64, 0, sT>>>(challenge_args(ckW[b]->scratch.result.template as<Pt>(), ckT->scratch.result.template as<Pt>(), b, b,
                                                                   FOLD_MODE_FOLD));
         k++;
-        LURK_CUDA_TRY(cudaEventRecord(ev_chal[b], sB));
+        LURK_CUDA_TRY(cudaEventRecord(ev_chal[b], sT));
+        if (sT != sB) LURK_CUDA_TRY(cudaStreamWaitEvent(sB, ev_chal[b], 0));
         fold_axpy_kernel<Fs><<<fold_grid(nz + rows, 256, 8), 256, 0, sB>>>(z1.as<Fs>(), z2[b].as<Fs>(), nz, e1.as<Fs>(), T.as<Fs>(), rows, r_dev.as<Fs>());
         k++;
         LURK_CUDA_TRY(cudaGetLastError());
@@ -704,14 +712,19 @@ struct FoldCtx final : FoldCtxBase {
             LURK_CUDA_TRY(cudaMemcpyAsync(&bad, bad_dev.p, sizeof bad, cudaMemcpyDeviceToHost, sB));
         }
         // commit(W1) with the W key, commit(E1) with the T key, exchanged and normalised like a step's commitments
-        LURK_TRY(msm_launch<C>(ckW[0], z1.p, cfg.n_w, LURK_FMT_MONTGOMERY, sB, false));
+        LURK_TRY(msm_launch<C>(ckChkW, z1.p, cfg.n_w, LURK_FMT_MONTGOMERY, sB, false));
         LURK_TRY(msm_launch<C>(ckChk, e1.p, rows, LURK_FMT_MONTGOMERY, sB, false));
-        fold_challenge_kernel<C><<<1, 64, 0, sB>>>(challenge_args(ckW[0]->scratch.result.template as<Pt>(), ckChk->scratch.result.template as<Pt>(), 0, D,
+        if (sT != sB) {                    // covers the empty-vector memsets, which stay on sB
+            LURK_CUDA_TRY(cudaEventRecord(ev_chal[D], sB));
+            LURK_CUDA_TRY(cudaStreamWaitEvent(sT, ev_chal[D], 0));
+        }
+        fold_challenge_kernel<C><<<1, 64, 0, sT>>>(challenge_args(ckChkW->scratch.result.template as<Pt>(), ckChk->scratch.result.template as<Pt>(), 0, D,
                                                                   FOLD_MODE_COMMIT_ONLY));
         LURK_CUDA_TRY(cudaGetLastError());
-        LURK_CUDA_TRY(cudaMemcpyAsync(h_rec[D], rec_dev[D].p, sizeof(Rec), cudaMemcpyDeviceToHost, sB));
+        LURK_CUDA_TRY(cudaMemcpyAsync(h_rec[D], rec_dev[D].p, sizeof(Rec), cudaMemcpyDeviceToHost, sT));
         Pt pts[2];
-        LURK_CUDA_TRY(cudaMemcpyAsync(pts, run_pts.p, sizeof pts, cudaMemcpyDeviceToHost, sB));
+        LURK_CUDA_TRY(cudaMemcpyAsync(pts, run_pts.p, sizeof pts, cudaMemcpyDeviceToHost, sT));
+        LURK_CUDA_TRY(cudaStreamSynchronize(sT));
         LURK_CUDA_TRY(cudaStreamSynchronize(sB));
         const Rec &r = *h_rec[D];
         if (r.status) { set_error("partial-commitment exchange timed out"); return LURK_ERR_CUDA; }
@@ -738,7 +751,7 @@ struct FoldCtx final : FoldCtxBase {
     }
 
     int sync() override {
-        for (cudaStream_t s : {sH, sK[0], sK[1], sK[2], sA, sB, sC, sAcc})
+        for (cudaStream_t s : {sH, sK[0], sK[1], sK[2], sA, sB, sC, sT})
             if (s) LURK_CUDA_TRY(cudaStreamSynchronize(s));
         return LURK_OK;
     }

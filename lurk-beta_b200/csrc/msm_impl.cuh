@@ -550,10 +550,11 @@ struct lurk_msm_ctx {
     bool pending_fixed = false;
     uint32_t pending_nq = 0, pending_K = 0;
     cudaEvent_t done = nullptr;
-    // optional SM partitioning (set by the fold context): the bucket-accumulation kernel -- the one throughput-shaped kernel
-    // of the pipeline -- is enqueued on `acc_stream` (a stream of another green context) between two events, the
-    // latency-shaped rest stays on the caller's stream
-    cudaStream_t acc_stream = nullptr;
+    // optional SM partitioning (set by the fold context): the one-warp finishing kernel (msm_horner_kernel) is enqueued on
+    // `tiny_stream` -- a stream of a small green-context partition reserved for the single-CTA kernels of the fold chain, so
+    // that they do not share an SM's multiplier pipe with thousands of bucket-accumulation warps.  Without read-back the
+    // result is then ready on `tiny_stream`, not on the caller's stream.
+    cudaStream_t tiny_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
@@ -642,24 +643,14 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
     msm_scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_sums, ntiles, tile_offsets);
     msm_scan_apply_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_offsets, ntiles, offsets);
     msm_scatter_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, key_stride, base_stride, offsets, cursor, sorted);
-    cudaStream_t sa = s;
-    if (ctx->acc_stream && ctx->acc_stream != s) {
-        sa = ctx->acc_stream;
-        LURK_CUDA_TRY(cudaEventRecord(ctx->ev_fork, s));
-        LURK_CUDA_TRY(cudaStreamWaitEvent(sa, ctx->ev_fork, 0));
-    }
-    if (ctx->profile) LURK_CUDA_TRY(cudaEventRecord(ctx->ev0, sa));
+    if (ctx->profile) LURK_CUDA_TRY(cudaEventRecord(ctx->ev0, s));
     if (fixed)
-        msm_accumulate_kernel<Fb, 5><<<(P.t1 + 127) / 128, 128, 0, sa>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
-                                                                        S.ppt[0].as<Pt>(), P.seg, P.t1);
+        msm_accumulate_kernel<Fb, 5><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
+                                                                       S.ppt[0].as<Pt>(), P.seg, P.t1);
     else
-        msm_accumulate_kernel<Fb, 4><<<(P.t1 + 127) / 128, 128, 0, sa>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
-                                                                        S.ppt[0].as<Pt>(), P.seg, P.t1);
-    if (ctx->profile) LURK_CUDA_TRY(cudaEventRecord(ctx->ev1, sa));
-    if (sa != s) {
-        LURK_CUDA_TRY(cudaEventRecord(ctx->ev_join, sa));
-        LURK_CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-    }
+        msm_accumulate_kernel<Fb, 4><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
+                                                                       S.ppt[0].as<Pt>(), P.seg, P.t1);
+    if (ctx->profile) LURK_CUDA_TRY(cudaEventRecord(ctx->ev1, s));
     launches += 6;
     // shrinking passes over the partial list: one throughput-shaped pass (8 entries per thread), then warp-cooperative
     // passes (32x per pass, 5 dependent additions each) until a single warp finishes
@@ -695,8 +686,17 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
         launches++;
     }
     if (fixed) {   // one bucket set: finish the weighted sum on the device (result stays resident for chained consumers)
-        msm_horner_kernel<Fb><<<1, 32, 0, s>>>(S.wins.as<Pt>(), P.nq, P.K, S.result.as<Pt>());
+        cudaStream_t st = ctx->tiny_stream ? ctx->tiny_stream : s;
+        if (st != s) {
+            LURK_CUDA_TRY(cudaEventRecord(ctx->ev_fork, s));
+            LURK_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+        }
+        msm_horner_kernel<Fb><<<1, 32, 0, st>>>(S.wins.as<Pt>(), P.nq, P.K, S.result.as<Pt>());
         launches++;
+        if (st != s && readback) {
+            LURK_CUDA_TRY(cudaEventRecord(ctx->ev_join, st));
+            LURK_CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+        }
     }
     ctx->last_launches = launches;
     LURK_CUDA_TRY(cudaGetLastError());

@@ -10,13 +10,18 @@ from torch.profiler import ProfilerActivity, profile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 
-wl = bench.FoldStepGPU(0, 1)
+if len(sys.argv) > 1:
+    bench.LIVE_SLOT_FRACTION = float(sys.argv[1])
+wl = bench.FoldStepGPU(0, 1, latency_sms=int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+wl.start(True)
 for _ in range(4):
-    wl.step()
+    wl.step(False)
+wl.drain()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(4):
-        wl.step()
+        wl.step(False)
+    wl.drain()
     torch.cuda.synchronize()
 prof.export_chrome_trace("gpurun_out/trace.json")
 ev = json.load(open("gpurun_out/trace.json"))["traceEvents"]
