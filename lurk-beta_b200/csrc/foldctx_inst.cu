@@ -51,7 +51,8 @@ struct FoldCtx final : FoldCtxBase {
     DevBuf z1, e1, T, mv1[3], z2[FOLD_MAX_DEPTH], mv2[FOLD_MAX_DEPTH][3];
     DevBuf csr_rp[3], csr_col[3], csr_val[3];
     CsrDev csr[3];
-    DevBuf ro_img, step_consts[FOLD_MAX_DEPTH], r_dev, seq_dev, rec_dev[FOLD_MAX_DEPTH + 1], run_pts, xchg, bad_dev;
+    DevBuf ro_img, step_consts[FOLD_MAX_DEPTH], r_dev, seq_dev, rec_dev[FOLD_MAX_DEPTH + 1], run_pts, xchg, bad_dev, dummy_w, dummy_p;
+    bool dummy_ready = false;
     Rec *h_rec[FOLD_MAX_DEPTH + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void *h_glue[FOLD_MAX_DEPTH] = {nullptr, nullptr, nullptr, nullptr};
     void *h_x2[FOLD_MAX_DEPTH] = {nullptr, nullptr, nullptr, nullptr};
@@ -497,9 +498,51 @@ struct FoldCtx final : FoldCtxBase {
         return LURK_OK;
     }
 
+    // The constant part of every fresh witness: D = the slot blocks of a step whose slots are all dummies (all-zero preimages),
+    // zero elsewhere.  Unused slots of a frame share one cached witness per slot type in the reference
+    // (src/lem/multiframe.rs:553-577), so W2 - D vanishes on every dummy slot: commit(W2) = commit(W2 - D) + commit(D) with
+    // commit(D) computed once here.  Built at the first stage A, when the slot batches are known.
+    int prepare_dummy() {
+        if (dummy_ready) return LURK_OK;
+        dummy_ready = true;
+        static const bool off = getenv("LURK_FOLD_NO_DUMMY_OFFSET") != nullptr;      // measurement aid
+        size_t nslots = 0;
+        for (auto &sb : batches) nslots += sb->count;
+        if (off || !nslots || !cfg.n_w) return LURK_OK;
+        LURK_TRY(dummy_w.alloc((size_t)cfg.n_w * sizeof(Fs)));
+        LURK_CUDA_TRY(cudaMemsetAsync(dummy_w.p, 0, (size_t)cfg.n_w * sizeof(Fs), sB));
+        for (auto &sb : batches) {
+            if (!sb->count) continue;
+            void *zeros = nullptr;
+            LURK_CUDA_TRY(cudaMallocAsync(&zeros, sb->bytes(), sB));
+            LURK_CUDA_TRY(cudaMemsetAsync(zeros, 0, sb->bytes(), sB));
+            int rc;
+            if (sb->arity) {
+                rc = launch_poseidon<Fs, true>(sb->arity, zeros, sb->count, dummy_w.p, LURK_FMT_MONTGOMERY, LURK_FMT_MONTGOMERY, sB, sb->d_offsets.as<uint64_t>());
+            } else {
+                uint32_t mod[8];
+                for (int i = 0; i < 8; i++) mod[i] = Fs::Params::MOD(i);
+                rc = launch_bitdecomp<Fs>(zeros, sb->count, dummy_w.p, bitdecomp_block_host(mod), LURK_FMT_MONTGOMERY, sB, sb->d_offsets.as<uint64_t>());
+            }
+            cudaFreeAsync(zeros, sB);
+            LURK_TRY(rc);
+        }
+        uint8_t pt[96];
+        LURK_TRY(msm_launch<C>(ckChkW, dummy_w.p, cfg.n_w, LURK_FMT_MONTGOMERY, sB, true));
+        LURK_TRY(msm_finish<C>(ckChkW, pt));
+        Fb z;
+        memcpy(z.v, pt + 64, 32);
+        if (z.is_zero()) return LURK_OK;               // commit(D) is the identity: nothing to gain
+        LURK_TRY(dummy_p.alloc(64));
+        LURK_CUDA_TRY(cudaMemcpy(dummy_p.p, pt, 64, cudaMemcpyHostToDevice));
+        for (int k = 0; k < D; k++) { ckW[k]->d_sub = dummy_w.p; ckW[k]->d_offset = dummy_p.p; }
+        return LURK_OK;
+    }
+
     // ------------------------------------------------------------------------------------------ stage A
     int stage_a(int b, int flags, int fmt) override {
         LURK_TRY(chk_b(b));
+        LURK_TRY(prepare_dummy());
         if (fmt != LURK_FMT_CANONICAL && fmt != LURK_FMT_MONTGOMERY) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
         if (b_pending[b]) { set_error("buffer %d: the previous step's result has not been collected", b); return LURK_ERR_ARG; }
         const bool staged = !(flags & FOLD_INPUTS_RESIDENT);

@@ -96,13 +96,17 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t k[8], int bit, in
 }
 
 template <class Fs>
-__global__ void __launch_bounds__(256) msm_count_kernel(const Fs *__restrict__ scalars, size_t n, int fmt, int c, int nwin, uint32_t key_stride,
-                                                        uint32_t *__restrict__ counts) {
+__global__ void __launch_bounds__(256) msm_count_kernel(const Fs *__restrict__ scalars, const Fs *__restrict__ sub, size_t n, int fmt, int c, int nwin,
+                                                        uint32_t key_stride, uint32_t *__restrict__ counts) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
     // all lanes walk the windows together so the warp-aggregation below sees converged lanes
     Fs k = Fs::zero();
-    if (live) { k = load_fe<Fs>(scalars + i); if (fmt == LURK_FMT_MONTGOMERY) k = k.to_canonical(); }
+    if (live) {
+        k = load_fe<Fs>(scalars + i);
+        if (sub) k = k - load_fe<Fs>(sub + i);       // commit(s) = commit(s - d) + commit(d): see lurk_msm_ctx::d_sub
+        if (fmt == LURK_FMT_MONTGOMERY) k = k.to_canonical();
+    }
     uint32_t carry = 0;
     const uint32_t half = 1u << (c - 1);
     const uint32_t lane = threadIdx.x & 31;
@@ -174,13 +178,17 @@ static __global__ void __launch_bounds__(1024) msm_scan_apply_kernel(const uint3
 }
 
 template <class Fs>
-__global__ void __launch_bounds__(256) msm_scatter_kernel(const Fs *__restrict__ scalars, size_t n, int fmt, int c, int nwin, uint32_t key_stride,
-                                                          uint32_t base_stride, const uint32_t *__restrict__ offsets,
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const Fs *__restrict__ scalars, const Fs *__restrict__ sub, size_t n, int fmt, int c, int nwin,
+                                                          uint32_t key_stride, uint32_t base_stride, const uint32_t *__restrict__ offsets,
                                                           uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
     Fs k = Fs::zero();
-    if (live) { k = load_fe<Fs>(scalars + i); if (fmt == LURK_FMT_MONTGOMERY) k = k.to_canonical(); }
+    if (live) {
+        k = load_fe<Fs>(scalars + i);
+        if (sub) k = k - load_fe<Fs>(sub + i);
+        if (fmt == LURK_FMT_MONTGOMERY) k = k.to_canonical();
+    }
     uint32_t carry = 0;
     const uint32_t half = 1u << (c - 1);
     const uint32_t lane = threadIdx.x & 31;
@@ -433,7 +441,8 @@ __global__ void __launch_bounds__(128) msm_slice_sum_kernel(const XYZZ<Fb> *__re
 // Horner walk -- this kernel sits on the fold's critical chain.  The result stays on the device (XYZZ, 128 bytes) for the
 // fold context's challenge kernel; lurk_msm_ctx_finish reads it back and normalises it on the host.
 template <class Fb>
-__global__ void __launch_bounds__(32) msm_horner_kernel(const XYZZ<Fb> *__restrict__ wins, uint32_t nq, uint32_t K, XYZZ<Fb> *__restrict__ out) {
+__global__ void __launch_bounds__(32) msm_horner_kernel(const XYZZ<Fb> *__restrict__ wins, uint32_t nq, uint32_t K, const Affine<Fb> *__restrict__ offset,
+                                                        XYZZ<Fb> *__restrict__ out) {
     const uint32_t lane = threadIdx.x;
     XYZZ<Fb> pt = XYZZ<Fb>::identity();
     if (lane < nq) pt = load_xyzz(wins + lane);
@@ -449,7 +458,10 @@ __global__ void __launch_bounds__(32) msm_horner_kernel(const XYZZ<Fb> *__restri
         const XYZZ<Fb> p2 = shfl_xor_xyzz(pt, d);
         pt.add(p2);
     }
-    if (lane == 0) store_xyzz(out, pt);
+    if (lane == 0) {
+        if (offset) pt.add_affine(load_affine(offset));      // + commit(d), see lurk_msm_ctx::d_sub
+        store_xyzz(out, pt);
+    }
 }
 
 // Fixed-base table: table[w * n + i] = 2^(c w) * bases[i], affine.  One thread per base walks the windows with c
@@ -555,6 +567,13 @@ struct lurk_msm_ctx {
     // that they do not share an SM's multiplier pipe with thousands of bucket-accumulation warps.  Without read-back the
     // result is then ready on `tiny_stream`, not on the caller's stream.
     cudaStream_t tiny_stream = nullptr;
+    // Optional constant part of the scalar vector (set by the fold context; device-resident results only): when most of a
+    // vector repeats a fixed vector d from call to call -- the dummy slot witnesses of a Lurk step (src/lem/multiframe.rs:553-577:
+    // unused slots share one cached witness) -- the context commits to s - d, whose entries vanish wherever s repeats d and
+    // are skipped by the bucket sort, and msm_horner_kernel adds the precomputed point commit(d).  d_sub: key-length vector in
+    // the scalar field (Montgomery); d_offset: one affine point.
+    const void *d_sub = nullptr;
+    const void *d_offset = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
@@ -638,11 +657,12 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
     const uint32_t key_stride = fixed ? 0u : P.nb;                 // fixed-base: all windows share one bucket set
     const uint32_t base_stride = fixed ? (uint32_t)ctx->n : 0u;     // ... and address table[w * n + i]
     const Affine<Fb> *bases = (const Affine<Fb> *)(fixed ? ctx->d_table : ctx->d_bases);
-    msm_count_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, key_stride, counts);
+    const Fs *sub = (!readback && fmt == LURK_FMT_MONTGOMERY) ? (const Fs *)ctx->d_sub : nullptr;
+    msm_count_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, sub, n, fmt, P.c, P.nwin, key_stride, counts);
     msm_scan_tile_sums_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_sums);
     msm_scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_sums, ntiles, tile_offsets);
     msm_scan_apply_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_offsets, ntiles, offsets);
-    msm_scatter_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, n, fmt, P.c, P.nwin, key_stride, base_stride, offsets, cursor, sorted);
+    msm_scatter_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, sub, n, fmt, P.c, P.nwin, key_stride, base_stride, offsets, cursor, sorted);
     if (ctx->profile) LURK_CUDA_TRY(cudaEventRecord(ctx->ev0, s));
     if (fixed)
         msm_accumulate_kernel<Fb, 5><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
@@ -691,7 +711,7 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
             LURK_CUDA_TRY(cudaEventRecord(ctx->ev_fork, s));
             LURK_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
         }
-        msm_horner_kernel<Fb><<<1, 32, 0, st>>>(S.wins.as<Pt>(), P.nq, P.K, S.result.as<Pt>());
+        msm_horner_kernel<Fb><<<1, 32, 0, st>>>(S.wins.as<Pt>(), P.nq, P.K, sub ? (const Affine<Fb> *)ctx->d_offset : nullptr, S.result.as<Pt>());
         launches++;
         if (st != s && readback) {
             LURK_CUDA_TRY(cudaEventRecord(ctx->ev_join, st));
