@@ -26,6 +26,7 @@ static constexpr int FOLD_MAX_WORLD = 16;
 static constexpr int FOLD_MAX_DEPTH = 4;
 static constexpr int FOLD_MAX_SPANS = 4;
 static constexpr int FOLD_RO_RATE = 24;            // Arecibo's RO: neptune sponge over PoseidonConstants<_, U24>
+static constexpr int FOLD_T_WINDOW = 18;           // widest window of the chain-critical commit(T) (measured: profiles/r2_t_window.md)
 
 // ----------------------------------------------------------------------------- fold kernels (witness field)
 struct CsrDev {
@@ -80,28 +81,43 @@ __global__ void __launch_bounds__(256) cross_term_dev_kernel(const F *__restrict
     }
 }
 
-// the fold: z1 += r z2 over (W, u, X) and E1 += r T, one launch; r from device memory (written by the challenge kernel)
+// the fold: z1 += r z2 over (W, u, X), E1 += r T and -- A, B, C being linear -- A z1 += r A z2, B z1 += r B z2, C z1 += r C z2
+// (which takes the three sparse products of the running instance off the chain), one launch; r from device memory (written
+// by the challenge kernel)
 template <class F>
-__global__ void __launch_bounds__(256) fold_axpy_kernel(F *z1, const F *__restrict__ z2, size_t nz, F *e1, const F *__restrict__ t, size_t nt,
-                                                        const F *__restrict__ rp) {
+struct FoldAxpyArgs {
+    F *dst[5];
+    const F *src[5];
+    size_t end[5];       // cumulative element counts
+};
+template <class F>
+__global__ void __launch_bounds__(256) fold_axpy_kernel(FoldAxpyArgs<F> a, const F *__restrict__ rp) {
     const F r = load_fe<F>(rp);
-    const size_t total = nz + nt;
+    const size_t total = a.end[4];
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        if (i < nz) store_fe(z1 + i, load_fe<F>(z1 + i) + r * load_fe<F>(z2 + i));
-        else { const size_t j = i - nz; store_fe(e1 + j, load_fe<F>(e1 + j) + r * load_fe<F>(t + j)); }
+        int v = 0;
+        while (i >= a.end[v]) v++;
+        const size_t j = v ? i - a.end[v - 1] : i;
+        store_fe(a.dst[v] + j, load_fe<F>(a.dst[v] + j) + r * load_fe<F>(a.src[v] + j));
     }
 }
 
-// relaxed R1CS residual: counts rows with az*bz != u*cz + e
+// relaxed R1CS residual: counts rows with az*bz != u*cz + e; with `kept` vectors (the incrementally folded A z, B z, C z) also
+// rows where those differ from the freshly computed products
 template <class F>
 __global__ void __launch_bounds__(256) relaxed_residual_kernel(const F *__restrict__ az, const F *__restrict__ bz, const F *__restrict__ cz,
-                                                               const F *__restrict__ e, const F *__restrict__ up, size_t n, unsigned long long *bad) {
+                                                               const F *__restrict__ e, const F *__restrict__ up, const F *__restrict__ kept_a,
+                                                               const F *__restrict__ kept_b, const F *__restrict__ kept_c, size_t n,
+                                                               unsigned long long *bad) {
     const F u = load_fe<F>(up);
     unsigned local = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const F lhs = load_fe<F>(az + i) * load_fe<F>(bz + i);
-        const F rhs = u * load_fe<F>(cz + i) + load_fe<F>(e + i);
-        local += lhs == rhs ? 0u : 1u;
+        const F a = load_fe<F>(az + i), b = load_fe<F>(bz + i), c = load_fe<F>(cz + i);
+        const F lhs = a * b;
+        const F rhs = u * c + load_fe<F>(e + i);
+        bool ok = lhs == rhs;
+        if (kept_a) ok = ok && a == load_fe<F>(kept_a + i) && b == load_fe<F>(kept_b + i) && c == load_fe<F>(kept_c + i);
+        local += ok ? 0u : 1u;
     }
     local = __reduce_add_sync(0xffffffffu, local);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(bad, (unsigned long long)local);

@@ -78,6 +78,7 @@ struct FoldCtx final : FoldCtxBase {
     bool a_recorded[FOLD_MAX_DEPTH] = {false, false, false, false};
     bool b_pending[FOLD_MAX_DEPTH + 1] = {false, false, false, false, false};
     bool running_set = false;
+    bool mv1_valid = false;           // mv1 = (A z1, B z1, C z1) is kept current by the fold itself
     unsigned launches_a = 0, launches_b = 0;
     int device = 0;
     // green contexts (optional SM partition)
@@ -191,6 +192,20 @@ struct FoldCtx final : FoldCtxBase {
         if (ck_t != ck_w) LURK_TRY(lurk_msm_ctx_precompute(ck_t));
         for (int b = 0; b < D; b++) LURK_TRY(lurk_msm_ctx_clone(ck_w, &ckW[b]));
         LURK_TRY(lurk_msm_ctx_clone(ck_t, &ckT));
+        {
+            // commit(T) sits on the sequential chain: a narrower window than the throughput optimum shortens the bucket
+            // reduction (2^(c-1) buckets on the critical path) at the price of a few more additions per scalar; the context
+            // gets its own table over exactly n_rows bases
+            static const int t_window_env = [] { const char *e = getenv("LURK_FOLD_T_WINDOW"); return e ? atoi(e) : 0; }();   // tuning aid
+            const int want = t_window_env ? t_window_env : std::min(ck_t->fixed_c, FOLD_T_WINDOW);
+            if (want != ck_t->fixed_c && c.n_rows) {
+                ckT->n = c.n_rows;
+                ckT->d_table = nullptr;
+                ckT->owns_table = false;
+                ckT->fixed_c = 0;
+                LURK_TRY(msm_precompute<C>(ckT, want));
+            }
+        }
         LURK_TRY(lurk_msm_ctx_clone(ck_t, &ckChk));
         LURK_TRY(lurk_msm_ctx_clone(ck_w, &ckChkW));     // check_running must not touch a prefetched commit(W2)
         for (int b = 0; b < D; b++) lurk_msm_ctx_set_profiling(ckW[b], 1);
@@ -466,6 +481,7 @@ struct FoldCtx final : FoldCtxBase {
         LURK_CUDA_TRY(cudaMemcpyAsync(run_pts.p, pts, sizeof pts, cudaMemcpyHostToDevice, sB));
         LURK_CUDA_TRY(cudaStreamSynchronize(sB));
         running_set = true;
+        mv1_valid = false;
         return LURK_OK;
     }
     int download_vec(uint8_t *dst, const void *src, size_t n, int fmt) {
@@ -648,6 +664,9 @@ struct FoldCtx final : FoldCtxBase {
         LURK_CUDA_TRY(cudaStreamWaitEvent(sB, ev_A[b], 0));
         LURK_CUDA_TRY(cudaMemcpyAsync(z1.p, z2[b].p, nz * sizeof(Fs), cudaMemcpyDeviceToDevice, sB));
         LURK_CUDA_TRY(cudaMemsetAsync(e1.p, 0, (size_t)cfg.n_rows * sizeof(Fs), sB));
+        for (int m = 0; m < 3 && cfg.n_rows; m++)
+            LURK_CUDA_TRY(cudaMemcpyAsync(mv1[m].p, mv2[b][m].p, (size_t)cfg.n_rows * sizeof(Fs), cudaMemcpyDeviceToDevice, sB));
+        mv1_valid = true;
         LURK_CUDA_TRY(cudaStreamWaitEvent(sT, ev_cw[b], 0));
         fold_challenge_kernel<C><<<1, 64, 0, sT>>>(challenge_args(ckW[b]->scratch.result.template as<Pt>(), nullptr, b, b, FOLD_MODE_COMMIT_ONLY));
         LURK_CUDA_TRY(cudaGetLastError());
@@ -675,11 +694,12 @@ struct FoldCtx final : FoldCtxBase {
         if (b_pending[b]) { set_error("buffer %d: the previous step's result has not been collected", b); return LURK_ERR_ARG; }
         unsigned k = 0;
         const size_t rows = cfg.n_rows;
-        if (rows) {
+        if (rows && !mv1_valid) {     // only after set_running: the fold keeps A z1, B z1, C z1 current by linearity
             spmv3_kernel<Fs><<<dim3(fold_grid(rows, 256, 8), 3), 256, 0, sB>>>(csr[0], csr[1], csr[2], rows, z1.as<Fs>(), mv1[0].as<Fs>(), mv1[1].as<Fs>(),
                                                                              mv1[2].as<Fs>());
             k++;
         }
+        mv1_valid = true;
         LURK_CUDA_TRY(cudaStreamWaitEvent(sB, ev_A[b], 0));
         if (rows) {
             cross_term_dev_kernel<Fs><<<fold_grid(rows, 256, 8), 256, 0, sB>>>(mv1[0].as<Fs>(), mv1[1].as<Fs>(), mv1[2].as<Fs>(), mv2[b][0].as<Fs>(),
@@ -700,8 +720,14 @@ struct FoldCtx final : FoldCtxBase {
         k++;
         LURK_CUDA_TRY(cudaEventRecord(ev_chal[b], sT));
         if (sT != sB) LURK_CUDA_TRY(cudaStreamWaitEvent(sB, ev_chal[b], 0));
-        fold_axpy_kernel<Fs><<<fold_grid(nz + rows, 256, 8), 256, 0, sB>>>(z1.as<Fs>(), z2[b].as<Fs>(), nz, e1.as<Fs>(), T.as<Fs>(), rows, r_dev.as<Fs>());
-        k++;
+        {
+            FoldAxpyArgs<Fs> ax;
+            ax.dst[0] = z1.as<Fs>(); ax.src[0] = z2[b].as<Fs>(); ax.end[0] = nz;
+            ax.dst[1] = e1.as<Fs>(); ax.src[1] = T.as<Fs>(); ax.end[1] = nz + rows;
+            for (int m = 0; m < 3; m++) { ax.dst[2 + m] = mv1[m].as<Fs>(); ax.src[2 + m] = mv2[b][m].as<Fs>(); ax.end[2 + m] = nz + (size_t)(2 + m) * rows; }
+            fold_axpy_kernel<Fs><<<fold_grid(ax.end[4], 256, 8), 256, 0, sB>>>(ax, r_dev.as<Fs>());
+            k++;
+        }
         LURK_CUDA_TRY(cudaGetLastError());
         LURK_CUDA_TRY(cudaEventRecord(ev_fold[b], sB));
         fold_recorded[b] = true;
@@ -746,12 +772,17 @@ struct FoldCtx final : FoldCtxBase {
         const size_t rows = cfg.n_rows;
         unsigned long long bad = 0;
         if (rows) {
+            // fresh A z, B z, C z into scratch; the vectors kept current by the folds (mv1) must equal them
+            Fs *fresh = nullptr;
+            LURK_CUDA_TRY(cudaMallocAsync((void **)&fresh, 3 * rows * sizeof(Fs), sB));
             LURK_CUDA_TRY(cudaMemsetAsync(bad_dev.p, 0, sizeof(unsigned long long), sB));
-            spmv3_kernel<Fs><<<dim3(fold_grid(rows, 256, 8), 3), 256, 0, sB>>>(csr[0], csr[1], csr[2], rows, z1.as<Fs>(), mv1[0].as<Fs>(), mv1[1].as<Fs>(),
-                                                                             mv1[2].as<Fs>());
-            relaxed_residual_kernel<Fs><<<fold_grid(rows, 256, 8), 256, 0, sB>>>(mv1[0].as<Fs>(), mv1[1].as<Fs>(), mv1[2].as<Fs>(), e1.as<Fs>(),
-                                                                                z1.as<Fs>() + cfg.n_w, rows, bad_dev.as<unsigned long long>());
-            LURK_CUDA_TRY(cudaGetLastError());
+            spmv3_kernel<Fs><<<dim3(fold_grid(rows, 256, 8), 3), 256, 0, sB>>>(csr[0], csr[1], csr[2], rows, z1.as<Fs>(), fresh, fresh + rows, fresh + 2 * rows);
+            relaxed_residual_kernel<Fs><<<fold_grid(rows, 256, 8), 256, 0, sB>>>(fresh, fresh + rows, fresh + 2 * rows, e1.as<Fs>(), z1.as<Fs>() + cfg.n_w,
+                                                                                mv1_valid ? mv1[0].as<Fs>() : nullptr, mv1[1].as<Fs>(), mv1[2].as<Fs>(), rows,
+                                                                                bad_dev.as<unsigned long long>());
+            cudaError_t e = cudaGetLastError();
+            cudaFreeAsync(fresh, sB);
+            LURK_CUDA_TRY(e);
             LURK_CUDA_TRY(cudaMemcpyAsync(&bad, bad_dev.p, sizeof bad, cudaMemcpyDeviceToHost, sB));
         }
         // commit(W1) with the W key, commit(E1) with the T key, exchanged and normalised like a step's commitments

@@ -90,7 +90,7 @@ int lurk_msm_ctx_precompute(lurk_msm_ctx *ctx) {
     std::lock_guard<std::mutex> g(ctx->mu);
     if (ctx->d_table || ctx->n == 0) return LURK_OK;
     if (ctx->pending) { set_error("a launch is pending on this context"); return LURK_ERR_ARG; }
-    return dispatch_curve(ctx->curve_id, [&](auto cv) { return msm_precompute<decltype(cv)>(ctx); });
+    return dispatch_curve(ctx->curve_id, [&](auto cv) { return msm_precompute<decltype(cv)>(ctx, 0); });
 }
 
 int lurk_msm_ctx_clone(lurk_msm_ctx *ctx, lurk_msm_ctx **out) {

@@ -802,10 +802,11 @@ int ctx_upload(lurk_msm_ctx *ctx, const uint8_t *bases, size_t n, int fmt) {
 
 // builds the fixed-base table of a context (see lurk_msm_ctx_precompute)
 template <class C>
-int msm_precompute(lurk_msm_ctx *ctx) {
+int msm_precompute(lurk_msm_ctx *ctx, int c_override) {
     using Fb = typename C::Base;
     LURK_TRY(ctx_check_device(ctx));
-    const int c = fixed_base_window(ctx->n);
+    const int c = c_override ? c_override : fixed_base_window(ctx->n);
+    if (c < 4 || c > 22) { set_error("window width %d out of range", c); return LURK_ERR_ARG; }
     const int nwin = C::Scalar::Params::NBITS / c + 1;
     if (nwin > MSM_MAX_TABLE_WINDOWS || (uint64_t)nwin * ctx->n >= (1ull << 31)) { set_error("commitment key too large for a fixed-base table"); return LURK_ERR_ARG; }
     void *t = nullptr;
@@ -826,12 +827,12 @@ int msm_precompute(lurk_msm_ctx *ctx) {
     template int msm_finish<C>(lurk_msm_ctx *, uint8_t *);                                         \
     template int msm_run<C>(lurk_msm_ctx *, const void *, size_t, int, uint8_t *, cudaStream_t);  \
     template int ctx_upload<C>(lurk_msm_ctx *, const uint8_t *, size_t, int);                      \
-    template int msm_precompute<C>(lurk_msm_ctx *);
+    template int msm_precompute<C>(lurk_msm_ctx *, int);
 #define LURK_MSM_EXTERN(C)                                                                                \
     extern template int msm_launch<C>(lurk_msm_ctx *, const void *, size_t, int, cudaStream_t, bool);    \
     extern template int msm_finish<C>(lurk_msm_ctx *, uint8_t *);                                         \
     extern template int msm_run<C>(lurk_msm_ctx *, const void *, size_t, int, uint8_t *, cudaStream_t);  \
     extern template int ctx_upload<C>(lurk_msm_ctx *, const uint8_t *, size_t, int);                      \
-    extern template int msm_precompute<C>(lurk_msm_ctx *);
+    extern template int msm_precompute<C>(lurk_msm_ctx *, int);
 
 }  // namespace lurk
