@@ -26,7 +26,7 @@ static constexpr int FOLD_MAX_WORLD = 16;
 static constexpr int FOLD_MAX_DEPTH = 4;
 static constexpr int FOLD_MAX_SPANS = 4;
 static constexpr int FOLD_RO_RATE = 24;            // Arecibo's RO: neptune sponge over PoseidonConstants<_, U24>
-static constexpr int FOLD_T_WINDOW = 18;           // widest window of the chain-critical commit(T) (measured: profiles/r2_t_window.md)
+static constexpr int FOLD_T_WINDOW = 16;           // widest window of the chain-critical commit(T) (measured: profiles/r2_ncu_summary.md)
 
 // ----------------------------------------------------------------------------- fold kernels (witness field)
 struct CsrDev {

@@ -197,7 +197,7 @@ struct FoldCtx final : FoldCtxBase {
             // reduction (2^(c-1) buckets on the critical path) at the price of a few more additions per scalar; the context
             // gets its own table over exactly n_rows bases
             static const int t_window_env = [] { const char *e = getenv("LURK_FOLD_T_WINDOW"); return e ? atoi(e) : 0; }();   // tuning aid
-            const int want = t_window_env ? t_window_env : std::min(ck_t->fixed_c, FOLD_T_WINDOW);
+            const int want = std::min(ck_t->fixed_c, t_window_env ? t_window_env : FOLD_T_WINDOW);   // never wider than the key's own choice
             if (want != ck_t->fixed_c && c.n_rows) {
                 ckT->n = c.n_rows;
                 ckT->d_table = nullptr;

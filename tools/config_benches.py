@@ -79,6 +79,24 @@ def poseidon_config2():
             del pre, out
 
 
+def poseidon_witness(logn=22):
+    """K3 at scale: the Poseidon *witness* expansion, 32 A in and 32 (A + 3 (8 t + R_P) + 1) out per slot"""
+    rng = np.random.default_rng(23)
+    n = 1 << logn
+    field = 0
+    for arity in (8, 4):
+        blk = lib.lurk_poseidon_witness_block(field, arity)
+        pre = torch.from_numpy(rand_elements(rng, n * arity, "lem")).cuda()
+        out = torch.empty(n * blk * 32, dtype=torch.uint8, device="cuda")
+        best, med = dev_time(lambda: chk(lib.lurk_poseidon_witness_batch_dev(field, arity, pre.data_ptr(), n, out.data_ptr(), 1, None)), reps=3, warm=1)
+        alg = n * (arity * 32 + blk * 32)
+        emit(config=f"2/K3: Poseidon slot witnesses of 2^{logn} preimages", field="bn254_fr", arity=arity, n=n, block_elems=int(blk), ms=round(med, 3),
+             mwitness_per_s=round(n / med / 1e3, 2), algorithmic_gb_s=round(alg / med / 1e6, 2), hbm_frac=round(alg / med / 1e6 / PEAK, 5),
+             output_gb=round(n * blk * 32 / 1e9, 2), bound="FMA-heavy (IMAD.WIDE) pipe; stores 12.9 KB / 9.5 KB per sponge")
+        del pre, out
+        torch.cuda.empty_cache()
+
+
 def msm_config3(logn=24, curve=2):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,6 +220,8 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.only in ("all", "poseidon"):
         poseidon_config2()
+    if a.only in ("all", "witness"):
+        poseidon_witness(a.logn if a.only == "witness" else 22)
     if a.only in ("all", "msm24"):
         msm_config3(a.logn)
     if a.only in ("all", "hbm"):
