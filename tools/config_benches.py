@@ -221,7 +221,7 @@ if __name__ == "__main__":
     if a.only in ("all", "poseidon"):
         poseidon_config2()
     if a.only in ("all", "witness"):
-        poseidon_witness(a.logn if a.only == "witness" else 22)
+        poseidon_witness(min(a.logn, 22))
     if a.only in ("all", "msm24"):
         msm_config3(a.logn)
     if a.only in ("all", "hbm"):
