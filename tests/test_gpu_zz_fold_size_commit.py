@@ -42,3 +42,17 @@ def test_plain_c_client_on_the_gpu(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     assert "c_abi_client ok" in out.stdout
+
+
+def test_plain_c_fold_driver_on_the_gpu(tmp_path):
+    """tests/csrc/fold_client.c on the GPU box: a four-step IVC chain through lurk_fold_ctx_* from plain C99 -- device-side
+    relaxed-R1CS check, u = 1 + sum of the challenges, checkpoint / resume -- with no Python, torch or oracle in the process"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe, libdir = str(tmp_path / "fold_client"), os.path.join(root, "lurk-beta_b200")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "csrc", "fold_client.c"),
+                           "-o", exe, "-L", libdir, "-llurk_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == "fold_client ok"

@@ -178,3 +178,15 @@ def test_ntt_root_of_unity_is_the_field_types_own(fieldlib, spec, field):
     assert s == spec.TWO_ADICITY[field] and root == spec.root_of_unity(field, s)
     assert pow(root, 1 << s, p) == 1 and pow(root, 1 << (s - 1), p) == p - 1
     assert root == PUBLISHED_ROOT_OF_UNITY.get(field, p - 1)
+
+
+def test_plain_c_fold_driver_fails_loudly_without_gpu(tmp_path):
+    """tests/csrc/fold_client.c (the fold context through plain C99): without a CUDA device the contexts cannot be created
+    and the driver reports it; on the GPU box the same program folds a chain (tests/test_gpu_zz_fold_size_commit.py)"""
+    exe = str(tmp_path / "fold_client")
+    libdir = os.path.join(ROOT, "lurk-beta_b200")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "csrc", "fold_client.c"),
+                           "-o", exe, "-L", libdir, "-llurk_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "fold_client ok" in out.stdout
