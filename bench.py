@@ -72,16 +72,19 @@ def small_vals(rng, n):
     return val.reshape(-1)
 
 
-def step_circuit(seed, frames, slot_elems=SLOT_ELEMS, glue=GLUE_PER_FRAME, cons=CONS_PER_FRAME, n_x=2, linear_fraction=0.02):
+def step_circuit(seed, frames, slot_elems=SLOT_ELEMS, glue=GLUE_PER_FRAME, cons=CONS_PER_FRAME, n_x=2, linear_fraction=0.02, bits=0):
     """Synthetic R1CS in the shape of the Lurk step circuit, satisfiable by construction AND with a dense cross term (as the
-    real circuit's: every constraint is a genuine product).  Per frame: `glue` defining rows (a_k . slots)(b_k . slots) = glue_k
-    -- the LEM-body aux stand-in -- and cons - glue further rows that re-state a definition k = row mod glue with other
-    coefficients, (l a_k . slots)(m b_k . slots) = l m glue_k, except a small fraction of linear rows (a . z) u = (a . z) that
-    also touch the public IO (their cross term vanishes identically).  Columns: frame-major W, then u, then X.  Values are
-    canonical small integers.  Returns [(row_ptr, col, val)] x 3, n_w, rows, the global row index of every defining row."""
+    real circuit's: every constraint is a genuine product).  Frame = [slot_elems free columns | glue defined columns | bits
+    boolean columns].  Per frame: `glue` defining rows (a_k . slots)(b_k . slots) = glue_k -- the LEM-body aux stand-in --,
+    cons - glue further rows that re-state a definition k = row mod glue with other coefficients, (l a_k . slots)(m b_k . slots)
+    = l m glue_k, except a small fraction of linear rows (a . z) u = (a . z) that also touch the public IO (their cross term
+    vanishes identically), and one booleanity row b * b = b per boolean column (the SHA-256 gadget's witness, config 4).
+    Columns: frame-major W, then u, then X.  Values are canonical small integers.
+    Returns [(row_ptr, col, val)] x 3, n_w, rows, the global row index of every defining row."""
     rng = np.random.default_rng(seed)
-    per = slot_elems + glue
-    n_w, rows = frames * per, frames * cons
+    per = slot_elems + glue + bits
+    rows_pf = cons + bits
+    n_w, rows = frames * per, frames * rows_pf
     # ---- the definitions of one frame layout (shared by all frames up to the column base)
     na = rng.integers(1, 4, size=glue)                       # non-zeros of a_k: 1..3
     nb = rng.integers(1, 3, size=glue)                       # non-zeros of b_k: 1..2
@@ -91,38 +94,45 @@ def step_circuit(seed, frames, slot_elems=SLOT_ELEMS, glue=GLUE_PER_FRAME, cons=
     b_col = rng.integers(0, slot_elems, size=int(b_ptr[-1]))
     a_cf = rng.integers(1, 4, size=int(a_ptr[-1]))
     b_cf = rng.integers(1, 4, size=int(b_ptr[-1]))
-    # ---- rows of one frame
-    local = np.arange(cons)
-    k = local % glue
-    is_lin = (local >= glue) & (rng.random(cons) < linear_fraction)
-    lam = np.where(local < glue, 1, rng.integers(1, 3, size=cons))
-    mu = np.where(local < glue, 1, rng.integers(1, 3, size=cons))
+    # ---- rows of one frame: [cons product / linear rows | bits booleanity rows]
+    local = np.arange(rows_pf)
+    is_bool = local >= cons
+    k = np.where(is_bool, 0, local % glue)
+    is_lin = (local >= glue) & ~is_bool & (rng.random(rows_pf) < linear_fraction)
+    own = is_lin | is_bool                                     # rows with their own entries instead of a definition's
+    lam = np.where(local < glue, 1, rng.integers(1, 3, size=rows_pf))
+    mu = np.where(local < glue, 1, rng.integers(1, 3, size=rows_pf))
+    bit_col = slot_elems + glue + (local - cons)               # valid where is_bool
 
-    def expand(ptr, col, cf, scale, lin_cols, lin_cf):
-        """per-frame CSR of rows taking definition k's entries scaled, or the linear row's own entries"""
-        cnt = np.where(is_lin, lin_cols.shape[1], ptr[k + 1] - ptr[k])
+    def expand(ptr, col, cf, scale, own_cols, own_cf, own_cnt):
+        """per-frame CSR of rows taking definition k's entries scaled, or the row's own entries (first own_cnt of them)"""
+        cnt = np.where(own, own_cnt, ptr[k + 1] - ptr[k])
         rp = np.concatenate([[0], np.cumsum(cnt)])
         cols = np.empty(int(rp[-1]), dtype=np.int64)
         vals = np.empty(int(rp[-1]), dtype=np.int64)
         r_of = np.repeat(local, cnt)
         within = np.arange(int(rp[-1])) - rp[r_of]
-        d = ~is_lin[r_of]
+        d = ~own[r_of]
         src = ptr[k[r_of[d]]] + within[d]
         cols[d] = col[src]
         vals[d] = cf[src] * scale[r_of[d]]
-        cols[~d] = lin_cols[r_of[~d], within[~d]]
-        vals[~d] = lin_cf[r_of[~d], within[~d]]
+        cols[~d] = own_cols[r_of[~d], within[~d]]
+        vals[~d] = own_cf[r_of[~d], within[~d]]
         return rp, cols, vals
 
-    # linear rows: two W columns of the frame + one public-IO column (marked -1 - j, resolved below), coefficient 1..3
-    lin_cols = np.stack([rng.integers(0, per, size=cons), rng.integers(0, per, size=cons), -1 - rng.integers(0, n_x, size=cons)], axis=1)
-    lin_cf = rng.integers(1, 4, size=(cons, 3))
-    U = -100                                                   # marker of the u column
-    fa = expand(a_ptr, a_col, a_cf, lam, lin_cols, lin_cf)
-    fb = expand(b_ptr, b_col, b_cf, mu, np.full((cons, 1), U), np.ones((cons, 1), dtype=np.int64))
-    # C: defining / restating rows -> lam * mu at the glue column; linear rows -> their A row
+    U = -100                                                   # marker of the u column; -1 - j marks public IO j
+    # A: linear rows = two W columns of the frame + one public-IO column; boolean rows = the bit column
+    lin_cols = np.stack([rng.integers(0, per, size=rows_pf), rng.integers(0, per, size=rows_pf), -1 - rng.integers(0, n_x, size=rows_pf)], axis=1)
+    lin_cf = rng.integers(1, 4, size=(rows_pf, 3))
+    a_own_cols = np.where(is_bool[:, None], bit_col[:, None], lin_cols)
+    a_own_cf = np.where(is_bool[:, None], 1, lin_cf)
+    fa = expand(a_ptr, a_col, a_cf, lam, a_own_cols, a_own_cf, np.where(is_bool, 1, 3))
+    # B: linear rows = u; boolean rows = the bit column
+    b_own_cols = np.where(is_bool, bit_col, U)[:, None]
+    fb = expand(b_ptr, b_col, b_cf, mu, b_own_cols, np.ones((rows_pf, 1), dtype=np.int64), np.ones(rows_pf, dtype=np.int64))
+    # C: defining / restating rows -> lam * mu at the glue column; linear rows -> their A row; boolean rows -> the bit column
     c_ptr = np.arange(glue + 1)
-    fc = expand(c_ptr, slot_elems + np.arange(glue), np.ones(glue, dtype=np.int64), lam * mu, lin_cols, lin_cf)
+    fc = expand(c_ptr, slot_elems + np.arange(glue), np.ones(glue, dtype=np.int64), lam * mu, a_own_cols, a_own_cf, np.where(is_bool, 1, 3))
 
     def tile(frame_csr):
         rp, cols, vals = frame_csr
@@ -135,24 +145,26 @@ def step_circuit(seed, frames, slot_elems=SLOT_ELEMS, glue=GLUE_PER_FRAME, cons=
         v[:, 0] = np.tile(vals, frames).astype(np.uint8)
         return all_rp, c.reshape(-1).astype(np.uint32), v.reshape(-1)
 
-    prod_rows = (np.arange(frames, dtype=np.int64)[:, None] * cons + np.arange(glue)[None, :]).reshape(-1)
+    prod_rows = (np.arange(frames, dtype=np.int64)[:, None] * rows_pf + np.arange(glue)[None, :]).reshape(-1)
     return [tile(fa), tile(fb), tile(fc)], n_w, rows, prod_rows
 
 
-def slot_offsets(frames):
-    """element offset of every slot block inside W, in the reference's frame layout (multiframe.rs:635-712)"""
+def slot_offsets(frames, per, slots, bd_per_frame, field=0):
+    """element offset of every slot block inside W, in the reference's frame layout (multiframe.rs:635-712): per frame
+    [slot blocks in slot order | body aux ...]; returns ([(arity, offsets)], slot elements per frame)"""
     import lurk_beta_b200 as L
     lib = L._capi.lib()
     out, cur = [], 0
-    f = np.arange(frames, dtype=np.uint64)[:, None] * AUX_PER_FRAME
-    for arity, per_frame in SLOTS:
-        blk = lib.lurk_poseidon_witness_block(0, arity)
-        out.append((arity, (f + cur + np.arange(per_frame, dtype=np.uint64)[None, :] * blk).reshape(-1)))
+    f = np.arange(frames, dtype=np.uint64)[:, None] * per
+    for arity, per_frame in slots:
+        blk = lib.lurk_poseidon_witness_block(field, arity)
+        out.append((arity, per_frame, (f + cur + np.arange(per_frame, dtype=np.uint64)[None, :] * blk).reshape(-1)))
         cur += per_frame * blk
-    blk = lib.lurk_bitdecomp_witness_block(0)
-    out.append((0, (f + cur + np.arange(BITDECOMP_PER_FRAME, dtype=np.uint64)[None, :] * blk).reshape(-1)))
-    assert cur + BITDECOMP_PER_FRAME * blk == SLOT_ELEMS
-    return out
+    if bd_per_frame:
+        blk = lib.lurk_bitdecomp_witness_block(field)
+        out.append((0, bd_per_frame, (f + cur + np.arange(bd_per_frame, dtype=np.uint64)[None, :] * blk).reshape(-1)))
+        cur += bd_per_frame * blk
+    return out, cur
 
 
 def to_mont(buf, p):
@@ -163,17 +175,24 @@ def to_mont(buf, p):
                          dtype=np.uint8).copy()
 
 
-def workload_config(world, scaling):
-    frames = RC * world if scaling == "weak" else RC
-    return {"workload": "fib rc=100 Nova IVC fold step on BN254/Grumpkin (benches/fibonacci.rs, configs[0]/metric config)",
-            "composed": "per fold, through lurk_fold_ctx_*: H2D of slot preimages + LEM-body aux; 2100 Poseidon slot witnesses + 300 bit-decomps "
-                        "per 100 frames; commit(W) 911900 terms; 6 SpMV + cross term over 1114100 rows; commit(T); Poseidon-sponge RO challenge; "
-                        "fold of (W,u,X), E and both commitments; the same fold of a 10^4-constraint secondary circuit on Grumpkin. "
-                        "LEM synthesis / augmented-circuit synthesis / reference Rust prover not included",
-            "frames_per_step": frames, "scaling": scaling, "live_slot_fraction": LIVE_SLOT_FRACTION,
-            "commitment_key": "2^21 synthetic BN254 G1 points per 100 frames ([i+1]G), sharded by frame; fixed-base window tables built once",
-            "l2": "inputs per step (128 MiB key, 1.7 GB window table, 64 MiB of vectors, 140 MiB CSR) exceed the 126 MB L2",
-            "parallelism": f"frames/bases sharded over {world} GPU(s); partial commitments exchanged through NVLink peer memory inside the challenge kernel"}
+def workload_config(world, scaling, workload="fib", rc=RC):
+    frames = rc * world if scaling == "weak" else rc
+    cfg = {"workload": "fib rc=100 Nova IVC fold step on BN254/Grumpkin (benches/fibonacci.rs, configs[0]/metric config)",
+           "composed": "per fold, through lurk_fold_ctx_*: H2D of slot preimages + LEM-body aux; 2100 Poseidon slot witnesses + 300 bit-decomps "
+                       "per 100 frames; commit(W) 911900 terms; cross term over 1114100 rows (A z, B z, C z of the running instance kept current by "
+                       "the fold); commit(T); Poseidon-sponge RO challenge; fold of (W,u,X), E and both commitments; the same fold of a "
+                       "10^4-constraint secondary circuit on Grumpkin. LEM synthesis / augmented-circuit synthesis / reference Rust prover not included",
+           "frames_per_step": frames, "scaling": scaling, "live_slot_fraction": LIVE_SLOT_FRACTION,
+           "commitment_key": "2^21 synthetic BN254 G1 points per 100 frames ([i+1]G), sharded by frame; fixed-base window tables built once",
+           "l2": "inputs per step (128 MiB key, 1.7 GB window table, 64 MiB of vectors, 140 MiB CSR) exceed the 126 MB L2",
+           "parallelism": f"frames/bases sharded over {world} GPU(s); partial commitments exchanged through NVLink peer memory inside the challenge kernel"}
+    if workload == "sha256_ivc":
+        cfg["workload"] = (f"examples/sha256_ivc.rs shape (configs[3]): rc={rc}, every frame = Lurk frame + inlined SHA-256 gadget (45000 boolean aux "
+                           "and booleanity constraints); |W| = rc * 54119, rows = rc * 56141; Nova IVC on BN254/Grumpkin")
+    elif workload == "trie_nivc":
+        cfg["workload"] = (f"benches/trie_nivc.rs shape (configs[4]): SuperNova NIVC, Lurk step circuit rc={rc} + trie-lookup coprocessor circuit "
+                           "(85 arity-8 Poseidon witnesses, src/coprocessor/trie/mod.rs:592-640) + secondary circuit; one fold of each per step")
+    return cfg
 
 
 class ClockSampler:
@@ -222,69 +241,142 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
-class FoldStepGPU:
-    """one rank's share of the fold step, driven through the C-ABI fold context"""
+# circuit shapes: (slots per frame, bit decompositions per frame, free host columns when there are no slots, glue, boolean
+# columns, product/linear constraints) -- frame = [slot blocks | glue | bits]
+LURK_FRAME = dict(slots=SLOTS, bd=BITDECOMP_PER_FRAME, free=0, glue=GLUE_PER_FRAME, bits=0, cons=CONS_PER_FRAME)
+SECONDARY = dict(slots=[], bd=0, free=SECONDARY_N - 1500, glue=1500, bits=0, cons=SECONDARY_N)
+# examples/sha256_ivc.rs (config 4): the SHA-256 gadget is inlined in every frame of the step circuit (src/coprocessor/sha256.rs:27-64):
+# ~45 k boolean aux and as many constraints per frame on top of the Lurk frame, rc = 10 (examples/sha256_ivc.rs:20)
+SHA256_FRAME = dict(slots=SLOTS, bd=BITDECOMP_PER_FRAME, free=0, glue=GLUE_PER_FRAME, bits=45_000, cons=CONS_PER_FRAME)
+# trie lookup coprocessor circuit (config 5; src/coprocessor/trie/mod.rs:592-640): 85 arity-8 Poseidon witnesses + path glue
+TRIE_LOOKUP = dict(slots=[(8, 85)], bd=0, free=0, glue=2_000, bits=0, cons=40_000)
 
-    def __init__(self, rank, world, scaling="weak", latency_sms=0, seed=0x6c75726b):
-        import torch
-        import lurk_beta_b200 as L
-        self.torch, self.L = torch, L
-        self.rank, self.world = rank, world
+
+class Instance:
+    """one circuit of the proof = one fold context, with the synthetic inputs of two distinct fresh instances in its pinned buffers"""
+
+    def __init__(self, torch, L, curve, shape, frames, ck_w, ck_t, world, rank, seed, live, x2, latency_sms=0):
+        self.torch, self.L, self.curve, self.frames = torch, L, curve, frames
+        self.p_w, self.p_base = (P_FR, P_FQ) if curve == CURVE else (P_FQ, P_FR)
+        self.field = 0 if curve == CURVE else 1
         M = L.FMT_MONTGOMERY
-        total_frames = RC * world if scaling == "weak" else RC
-        f0, f1 = (total_frames * rank) // world, (total_frames * (rank + 1)) // world
-        self.frames = f1 - f0
-        # the same circuit on every rank count: rows / columns of this rank's frames (frame-local columns + the (u, X) tail)
-        mats, self.nW, self.nT, prod_rows = step_circuit(seed + 1000 * rank, self.frames)
-        self.prod_rows = prod_rows
-        # ---- commitment key: this rank's slices of the global key [i+1]G in the reference's layout (W index = frame * 9119 + j,
-        # T / E index = frame * 11141 + j).  One resident 2^21-point key serves both when nothing is sharded.
-        if world == 1:
-            self.ck_w = self.ck_t = L.CommitmentKey(CURVE, L.synthetic_bases(CURVE, 1 << 21, fmt=M), fmt=M)
-        else:
-            self.ck_w = L.CommitmentKey(CURVE, L.synthetic_bases(CURVE, self.nW, start=f0 * AUX_PER_FRAME, fmt=M), fmt=M)
-            self.ck_t = L.CommitmentKey(CURVE, L.synthetic_bases(CURVE, self.nT, start=f0 * CONS_PER_FRAME, fmt=M), fmt=M)
-        self.ctx = L.NovaFoldContext(CURVE, self.ck_w, self.nW, 2, mats, depth=2, fmt=L.FMT_CANONICAL, ck_t=self.ck_t, world=world, rank=rank,
+        layout, slot_elems = slot_offsets(frames, 0, shape["slots"], shape["bd"], self.field)     # first pass: sizes only
+        self.slot_elems = slot_elems or shape["free"]
+        self.glue, self.bits = shape["glue"], shape["bits"]
+        self.per = self.slot_elems + self.glue + self.bits
+        layout, _ = slot_offsets(frames, self.per, shape["slots"], shape["bd"], self.field)
+        self.mats, self.nW, self.nT, self.prod_rows = step_circuit(seed, frames, slot_elems=self.slot_elems, glue=self.glue, cons=shape["cons"],
+                                                                   bits=self.bits)
+        self.ctx = L.NovaFoldContext(curve, ck_w, self.nW, 2, self.mats, depth=2, fmt=L.FMT_CANONICAL, ck_t=ck_t, world=world, rank=rank,
                                      latency_sms=latency_sms)
-        self.mats = mats
-        self.batch = [(arity, self.ctx.add_slot_batch(arity, offs)) for arity, offs in slot_offsets(self.frames)]
-        self.ctx.set_spans([(SLOT_ELEMS, GLUE_PER_FRAME, AUX_PER_FRAME, self.frames)])
-        # ---- secondary circuit (Grumpkin): whole witness from the host, replicated on every rank
-        mats2, self.nW2, self.nT2, prod2 = step_circuit(seed + 7, 1, slot_elems=SECONDARY_N - 1500, glue=1500, cons=SECONDARY_N)
-        self.ck2 = L.CommitmentKey(CURVE2, L.synthetic_bases(CURVE2, 1 << 14, fmt=M), fmt=M)
-        self.ctx2 = L.NovaFoldContext(CURVE2, self.ck2, self.nW2, 2, mats2, depth=2, fmt=L.FMT_CANONICAL)
-        self.ctx2.set_spans([(0, self.nW2, self.nW2, 1)])
-        self.mats2, self.prod2 = mats2, prod2
-        # ---- synthetic inputs of one step, written once into the pinned buffers of both fresh-instance buffers (Montgomery,
-        # the in-memory form of halo2curves); the X / RO constants are identical on every rank (the challenge must agree)
-        rng = np.random.default_rng(seed + 17 * rank)
-        common = np.random.default_rng(seed + 99)
-        self.X2 = [int(common.integers(1, 2**62)) * int(common.integers(1, 2**62)) for _ in range(2)]
-        self.X2s = [int(common.integers(1, 2**62)) * int(common.integers(1, 2**62)) for _ in range(2)]
-        # every input is handed over in Montgomery form (the in-memory form of halo2curves' field types); the random bytes
-        # below are < p, i.e. valid Montgomery representatives of uniformly random elements.  The two fresh-instance buffers
-        # get DIFFERENT inputs: folding the same instance over and over would make every cross term vanish identically.
-        ro = self._ro_consts(self.X2, P_FQ)
+        self.batch = [(arity, per_frame, self.ctx.add_slot_batch(arity, offs)) for arity, per_frame, offs in layout]
+        self.has_slots = bool(self.batch)
+        if self.has_slots:
+            self.ctx.set_spans([(self.slot_elems, self.glue + self.bits, self.per, frames)])
+        else:
+            self.ctx.set_spans([(0, self.nW, self.nW, 1)])          # the whole witness comes from the host
+        self.x2 = x2
+        rng = np.random.default_rng(seed + 1)
+        one = to_mont(FoldStepGPU._pack([1]), self.p_w)
+        # Every input is handed over in Montgomery form (the in-memory form of halo2curves' field types); random bytes < p are
+        # valid Montgomery representatives of uniformly random elements.  The two fresh-instance buffers get DIFFERENT inputs:
+        # folding the same instance over and over would make every cross term vanish identically.
         for b in range(2):
-            for arity, idx in self.batch:
-                n = self.frames * (dict(SLOTS).get(arity, BITDECOMP_PER_FRAME))
+            for arity, per_frame, idx in self.batch:
+                n = frames * per_frame
                 if arity:
                     x = rand_elements(rng, n * arity).reshape(n, arity * 32)
-                    x[rng.random(n) >= LIVE_SLOT_FRACTION] = 0
+                    x[rng.random(n) >= live] = 0
                     self.ctx.host_buffer(b, idx)[:] = x.reshape(-1)
                 else:
                     self.ctx.host_buffer(b, idx)[:] = rand_elements(rng, n, "witness")
-            self.ctx.host_buffer(b, L._capi.FOLD_BUF_X2)[:] = to_mont(self._pack(self.X2), P_FR)
-            self.ctx.host_buffer(b, L._capi.FOLD_BUF_RO)[:] = ro
-            # run the slot kernels once to learn the slot columns, then define the LEM-body aux from them (defining rows)
-            self._derive_glue(self.ctx, b, self.mats, self.prod_rows, self.nW, self.nT, P_FR, slots=True)
-            self.ctx2.host_buffer(b, L._capi.FOLD_BUF_GLUE)[:] = to_mont(rand_elements(rng, self.nW2, "witness"), P_FQ)
-            self.ctx2.host_buffer(b, L._capi.FOLD_BUF_X2)[:] = to_mont(self._pack(self.X2s), P_FQ)
-            self.ctx2.host_buffer(b, L._capi.FOLD_BUF_RO)[:] = self._ro_consts(self.X2s, P_FR)
-            self._derive_glue(self.ctx2, b, self.mats2, self.prod2, self.nW2, self.nT2, P_FQ, slots=False)
-        self.h2d_bytes = sum(self.ctx.host_buffer(0, w).size for w in [i for _, i in self.batch] + [-1, -2, -3]) + \
-            sum(self.ctx2.host_buffer(0, w).size for w in (-1, -2, -3))
-        self.d2h_bytes = 2 * 448                         # the two result records
+            host = self.ctx.host_buffer(b, L._capi.FOLD_BUF_GLUE)
+            rows = host.reshape(frames, -1)                          # per frame: [glue | bits] or [free | glue | bits]
+            row_elems = rows.shape[1] // 32
+            if not self.has_slots:
+                rows[:, :self.slot_elems * 32] = rand_elements(rng, frames * self.slot_elems, "witness").reshape(frames, -1)
+            if self.bits:
+                bitv = np.zeros((frames, self.bits, 32), dtype=np.uint8)
+                bitv[rng.random((frames, self.bits)) < 0.5] = one
+                rows[:, (row_elems - self.bits) * 32:] = bitv.reshape(frames, -1)
+            self.ctx.host_buffer(b, L._capi.FOLD_BUF_X2)[:] = to_mont(FoldStepGPU._pack(x2), self.p_w)
+            ro = np.zeros((24, 32), dtype=np.uint8)
+            for pos, v in ((0, PP_DIGEST), (4, x2[0]), (5, x2[1])):
+                ro[pos] = FoldStepGPU._pack([v])
+            self.ctx.host_buffer(b, L._capi.FOLD_BUF_RO)[:] = to_mont(ro.reshape(-1), self.p_base)
+            self._derive_glue(b)
+        self.h2d_bytes = sum(self.ctx.host_buffer(0, w).size for w in [i for _, _, i in self.batch] + [-1, -2, -3])
+
+    def _derive_glue(self, b):
+        """setup: make the fresh instance satisfy the circuit -- glue_g = (A_g . z)(B_g . z) for the defining rows, computed with
+        the library's own SpMV / cross-term kernels on the device from the slot columns the slot kernels produce"""
+        t, L, ctx = self.torch, self.L, self.ctx
+        lib = L._capi.lib()
+        M = L.FMT_MONTGOMERY
+        ctx.stage_a(b, fmt=M)          # with the glue still zero: fills the slot columns of W2 / uploads the free columns
+        ctx.sync()
+        z2 = ctx.device_view(b, L._capi.FOLD_BUF_W2)
+        dev = lambda a: t.from_numpy(np.ascontiguousarray(a)).cuda()
+        out = []
+        for rp, col, val in self.mats[:2]:
+            y = t.empty(self.nT * 32, dtype=t.uint8, device="cuda")
+            d = (dev(rp), dev(col), dev(to_mont_small(val, self.p_w)))
+            L._capi.check(lib.lurk_spmv_csr_dev(self.field, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), self.nT, z2.data_ptr(), y.data_ptr(), None))
+            out.append(y)
+        zero = t.zeros(self.nT * 32, dtype=t.uint8, device="cuda")
+        prod = t.empty(self.nT * 32, dtype=t.uint8, device="cuda")
+        z32 = np.zeros(32, dtype=np.uint8)
+        L._capi.check(lib.lurk_cross_term_dev(self.field, out[0].data_ptr(), zero.data_ptr(), zero.data_ptr(), zero.data_ptr(), out[1].data_ptr(),
+                                              zero.data_ptr(), L._capi.np_ptr(z32), L._capi.np_ptr(z32), self.nT, prod.data_ptr(), None))
+        t.cuda.synchronize()
+        glue = prod.view(self.nT, 32)[dev(self.prod_rows.astype(np.int64))].cpu().numpy().reshape(self.frames, self.glue * 32)
+        rows = ctx.host_buffer(b, L._capi.FOLD_BUF_GLUE).reshape(self.frames, -1)
+        g0 = 0 if self.has_slots else self.slot_elems
+        rows[:, g0 * 32:(g0 + self.glue) * 32] = glue
+        del z2
+
+
+class FoldStepGPU:
+    """one rank's share of the fold step of a workload, driven through the C-ABI fold context"""
+
+    def __init__(self, rank, world, scaling="weak", latency_sms=0, seed=0x6c75726b, workload="fib", rc=None):
+        import torch
+        import lurk_beta_b200 as L
+        self.torch, self.L = torch, L
+        self.rank, self.world, self.workload = rank, world, workload
+        M = L.FMT_MONTGOMERY
+        shape = SHA256_FRAME if workload == "sha256_ivc" else LURK_FRAME
+        self.rc = rc or {"fib": RC, "sha256_ivc": 10, "trie_nivc": 400}[workload]
+        total_frames = self.rc * world if scaling == "weak" else self.rc
+        f0, f1 = (total_frames * rank) // world, (total_frames * (rank + 1)) // world
+        self.frames = f1 - f0
+        per = SLOT_ELEMS + shape["glue"] + shape["bits"]
+        rows_pf = shape["cons"] + shape["bits"]
+        nW, nT = self.frames * per, self.frames * rows_pf
+        # ---- commitment key: this rank's slices of the global key [i+1]G in the reference's layout (W index = frame * per + j,
+        # T / E index = frame * rows_per_frame + j).  One resident power-of-two key serves both when nothing is sharded.
+        if world == 1:
+            n_key = 1 << max(14, (max(nW, nT) - 1).bit_length())
+            self.ck_w = self.ck_t = L.CommitmentKey(CURVE, L.synthetic_bases(CURVE, n_key, fmt=M), fmt=M)
+        else:
+            self.ck_w = L.CommitmentKey(CURVE, L.synthetic_bases(CURVE, nW, start=f0 * per, fmt=M), fmt=M)
+            self.ck_t = L.CommitmentKey(CURVE, L.synthetic_bases(CURVE, nT, start=f0 * rows_pf, fmt=M), fmt=M)
+        common = np.random.default_rng(seed + 99)                 # X / RO constants are identical on every rank (the challenge must agree)
+        mk_x = lambda: [int(common.integers(1, 2**62)) * int(common.integers(1, 2**62)) for _ in range(2)]
+        self.inst = [Instance(torch, L, CURVE, shape, self.frames, self.ck_w, self.ck_t, world, rank, seed + 1000 * rank, LIVE_SLOT_FRACTION, mk_x(),
+                              latency_sms)]
+        if workload == "trie_nivc":
+            # the coprocessor circuit is small: replicated on every rank (world = 1 context), one lookup per Lurk step
+            ck = self.ck_w if world == 1 else L.CommitmentKey(CURVE, L.synthetic_bases(CURVE, 1 << 17, fmt=M), fmt=M)
+            self.ck_trie = ck
+            self.inst.append(Instance(torch, L, CURVE, TRIE_LOOKUP, 1, ck, ck, 1, 0, seed + 5, 1.0, mk_x()))
+        # the secondary circuit of the cycle (Grumpkin): whole witness from the host, replicated on every rank
+        self.ck2 = L.CommitmentKey(CURVE2, L.synthetic_bases(CURVE2, 1 << 14, fmt=M), fmt=M)
+        self.inst.append(Instance(torch, L, CURVE2, SECONDARY, 1, self.ck2, self.ck2, 1, 0, seed + 7, 1.0, mk_x()))
+        self.ctx = self.inst[0].ctx
+        self.nW, self.nT, self.X2 = self.inst[0].nW, self.inst[0].nT, self.inst[0].x2
+        self.h2d_bytes = sum(i.h2d_bytes for i in self.inst)
+        self.d2h_bytes = 448 * len(self.inst)              # the result records
         self.step_index = 0
         self.started = False
         torch.cuda.synchronize()
@@ -293,76 +385,42 @@ class FoldStepGPU:
     def _pack(vals):
         return np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), dtype=np.uint8).copy()
 
-    def _ro_consts(self, X2, p_base):
-        ro = np.zeros((24, 32), dtype=np.uint8)
-        for pos, v in ((0, PP_DIGEST), (4, X2[0]), (5, X2[1])):
-            ro[pos] = self._pack([v])
-        return to_mont(ro.reshape(-1), p_base)
-
-    def _derive_glue(self, ctx, b, mats, prod_rows, n_w, n_rows, p, slots):
-        """setup: make the fresh instance satisfy the circuit -- glue_g = (A_g . z)(B_g . z) for the product rows, computed with
-        the library's own SpMV / cross-term kernels on the device from the slot columns the slot kernels produce"""
-        t, L = self.torch, self.L
-        lib = L._capi.lib()
-        M = L.FMT_MONTGOMERY
-        field = 0 if p == P_FR else 1
-        ctx.stage_a(b, fmt=M)          # with the glue still zero: fills the slot columns of W2 / uploads the dense witness
-        ctx.sync()
-        z2 = ctx.device_view(b, L._capi.FOLD_BUF_W2)
-        dev = lambda a: t.from_numpy(np.ascontiguousarray(a)).cuda()
-        out = []
-        for rp, col, val in mats[:2]:
-            y = t.empty(n_rows * 32, dtype=t.uint8, device="cuda")
-            d = (dev(rp), dev(col), dev(to_mont_small(val, p)))
-            L._capi.check(lib.lurk_spmv_csr_dev(field, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), n_rows, z2.data_ptr(), y.data_ptr(), None))
-            out.append(y)
-        zero = t.zeros(n_rows * 32, dtype=t.uint8, device="cuda")
-        prod = t.empty(n_rows * 32, dtype=t.uint8, device="cuda")
-        z32 = np.zeros(32, dtype=np.uint8)
-        L._capi.check(lib.lurk_cross_term_dev(field, out[0].data_ptr(), zero.data_ptr(), zero.data_ptr(), zero.data_ptr(), out[1].data_ptr(),
-                                              zero.data_ptr(), L._capi.np_ptr(z32), L._capi.np_ptr(z32), n_rows, prod.data_ptr(), None))
-        t.cuda.synchronize()
-        glue = prod.view(n_rows, 32)[dev(prod_rows.astype(np.int64))].cpu().numpy().reshape(-1)
-        if slots:
-            ctx.host_buffer(b, L._capi.FOLD_BUF_GLUE)[:] = glue
-        else:
-            # secondary: the glue columns are the tail of the dense witness
-            ctx.host_buffer(b, L._capi.FOLD_BUF_GLUE)[(n_w - glue.size // 32) * 32:] = glue
-        del z2
-
     # ------------------------------------------------------------------------------------------ the step loop
     def start(self, staged):
         """RecursiveSNARK::new on buffer 0, stage A of the first fold on buffer 1"""
-        for c in (self.ctx, self.ctx2):
-            c.stage_a(0, resident=not staged, fmt=self.L.FMT_MONTGOMERY)
-            c.init_running(0)
-            c.stage_a(1, resident=not staged, fmt=self.L.FMT_MONTGOMERY)
-        for c in (self.ctx, self.ctx2):
-            c.collect(0)
+        M = self.L.FMT_MONTGOMERY
+        for i in self.inst:
+            i.ctx.stage_a(0, resident=not staged, fmt=M)
+            i.ctx.init_running(0)
+            i.ctx.stage_a(1, resident=not staged, fmt=M)
+        for i in self.inst:
+            i.ctx.collect(0)
         self.step_index = 1
         self.uncollected = None
         self.started = True
 
     def step(self, staged):
-        """one fold: enqueue stage B of step i, collect step i-1's record, enqueue stage A of step i+1 into the freed buffer"""
-        i = self.step_index
-        b = i & 1
-        self.ctx.stage_b_launch(b)
-        self.ctx2.stage_b_launch(b)
+        """one fold of every circuit: enqueue stage B of step i, collect step i-1's records, enqueue stage A of step i+1 into the
+        freed buffers"""
+        k = self.step_index
+        b = k & 1
+        M = self.L.FMT_MONTGOMERY
+        for i in self.inst:
+            i.ctx.stage_b_launch(b)
         if self.uncollected is not None:
-            self.last = (self.ctx.collect(self.uncollected), self.ctx2.collect(self.uncollected))
+            self.last = [i.ctx.collect(self.uncollected) for i in self.inst]
         self.uncollected = b
-        self.ctx.stage_a(b ^ 1, resident=not staged, fmt=self.L.FMT_MONTGOMERY)
-        self.ctx2.stage_a(b ^ 1, resident=not staged, fmt=self.L.FMT_MONTGOMERY)
-        self.step_index = i + 1
+        for i in self.inst:
+            i.ctx.stage_a(b ^ 1, resident=not staged, fmt=M)
+        self.step_index = k + 1
 
     def drain(self):
         """collect the last fold (the prefetched stage A of the step after it stays un-folded: it is extra work inside the region)"""
         if self.uncollected is not None:
-            self.last = (self.ctx.collect(self.uncollected), self.ctx2.collect(self.uncollected))
+            self.last = [i.ctx.collect(self.uncollected) for i in self.inst]
             self.uncollected = None
-        self.ctx.sync()
-        self.ctx2.sync()
+        for i in self.inst:
+            i.ctx.sync()
 
 
 def to_mont_small(val, p):
@@ -373,22 +431,20 @@ def to_mont_small(val, p):
 
 
 def verify_full_size(wl, rank):
-    """outside the timed region: (1) the device-side relaxed-R1CS check of the running instance after real folds, on every rank
+    """outside the timed region: (1) the device-side relaxed-R1CS check of every running instance after real folds, on every rank
     (collective when the key is sharded); (2) rank 0 of an unsharded run: one full-size fold against the CPU oracle."""
-    out = {}
-    bad, okw, oke = wl.ctx.check_running()
-    bad2, okw2, oke2 = wl.ctx2.check_running()
-    out["relaxed_r1cs_bad_rows"] = int(bad) + int(bad2)
-    out["folded_commitments_open"] = bool(okw and oke and okw2 and oke2)
-    if wl.world == 1 and rank == 0:
+    out = {"relaxed_r1cs_bad_rows": 0, "folded_commitments_open": True}
+    for i in wl.inst:
+        bad, okw, oke = i.ctx.check_running()
+        out["relaxed_r1cs_bad_rows"] += int(bad)
+        out["folded_commitments_open"] = bool(out["folded_commitments_open"] and okw and oke)
+    if wl.world == 1 and rank == 0 and max(wl.nW, wl.nT) <= 5_000_000:
         from oracle import capi as oracle, spec, nifs   # checker only
         L = wl.L
-        th = os.cpu_count() or 1
+        th = host_threads()
         rec = wl.last[0]
         ctx = wl.ctx
         b = (wl.step_index - 1) & 1
-        R = 1 << 256
-        unmont = lambda buf, p: nifs.pack([x * pow(R, -1, p) % p for x in nifs.ints(buf)])
         W2 = ctx.read_device(b, L._capi.FOLD_BUF_W2)[:wl.nW * 32]
         T = ctx.read_device(0, L._capi.FOLD_BUF_T)
         # Montgomery -> canonical on the device (library kernel), then host
@@ -403,8 +459,10 @@ def verify_full_size(wl, rank):
         want_w = oracle.msm(CURVE, bases, W2c, nthreads=th)
         want_t = oracle.msm(CURVE, bases, Tc, nthreads=th)
         r, h = spec.ro_squeeze(1, spec.nifs_absorb_list(PP_DIGEST, nifs.point_of(want_w), wl.X2, nifs.point_of(want_t)))
+        nz_t = int(np.count_nonzero(Tc.reshape(-1, 32).any(axis=1)))
         out["oracle_fold"] = {"comm_W": bool(np.array_equal(rec.comm_W, want_w)), "comm_T": bool(np.array_equal(rec.comm_T, want_t)),
-                              "challenge": int.from_bytes(rec.r.tobytes(), "little") == r, "terms": [wl.nW, wl.nT]}
+                              "challenge": int.from_bytes(rec.r.tobytes(), "little") == r, "terms": [wl.nW, wl.nT],
+                              "cross_term_nonzero_fraction": round(nz_t / max(1, wl.nT), 4)}
     return out
 
 
@@ -453,7 +511,7 @@ def run_gpu(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    wl = FoldStepGPU(rank, world, scaling=args.scaling, latency_sms=args.latency_sms)
+    wl = FoldStepGPU(rank, world, scaling=args.scaling, latency_sms=args.latency_sms, workload=args.workload, rc=args.rc)
     wl.ctx.connect()          # exchange-buffer handles through the process group (setup only; the steps never call NCCL)
 
     def barrier():
@@ -485,21 +543,21 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     ms = timed(False, args.steps)
-    st = wl.ctx.stats()
-    st2 = wl.ctx2.stats()
+    stats = [i.ctx.stats() for i in wl.inst]
+    st = stats[0]
     ms_e2e = timed(True, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     # the dominant kernel with nothing else on the GPU (inside the step it overlaps other streams' kernels)
     iso = []
     wl.ck_t.set_profiling(True)
-    tbuf, tn = wl.ctx.device_buffer(0, wl.L._capi.FOLD_BUF_T)
+    tbuf, tn = wl.ctx.device_buffer(0, wl.L._capi.FOLD_BUF_E1)     # the running error vector: dense, full-width scalars
     for _ in range(5):
         wl.ck_t.launch_device(tbuf, wl.nT, fmt=wl.L.FMT_MONTGOMERY, stream=0)
         wl.ck_t.finish()
         iso.append(wl.ck_t.last_profile()[0])
     iso = iso[2:]
 
-    frames_total = RC * world if args.scaling == "weak" else RC
+    frames_total = wl.rc * world if args.scaling == "weak" else wl.rc
     iters = frames_total * args.steps
     value = iters / (ms / 1e3)
     e2e = iters / (ms_e2e / 1e3)
@@ -513,12 +571,12 @@ def run_gpu(args):
         iso_ms = sum(iso) / max(1, len(iso))
         terms = wl.nT
         achieved = terms * 96 / (iso_ms / 1e3) / 1e9 if iso_ms > 0 else 0.0
-        launches = st["launches_a"] + st["launches_b"] + st2["launches_a"] + st2["launches_b"]
+        launches = sum(x["launches_a"] + x["launches_b"] for x in stats)
         out = {
             "metric": METRIC, "value": round(value, 2), "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4),
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery integers)",
-            "data": "synthetic", "config": workload_config(world, args.scaling),
+            "data": "synthetic", "config": workload_config(world, args.scaling, args.workload, wl.rc),
             "e2e": {"value": round(e2e, 2), "unit": "iterations/s", "h2d_bytes_per_step": int(wl.h2d_bytes),
                     "d2h_bytes_per_step": int(wl.d2h_bytes), "ms_per_step": round(ms_e2e / args.steps, 4)},
             "gpu_launches": int(launches * args.steps),
@@ -539,7 +597,7 @@ def run_gpu(args):
         }
         if args.latency_sms:
             out["config"]["sm_partition"] = f"{args.latency_sms} SMs reserved for the latency-shaped kernels (green contexts)"
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "fib":
             out["cpu_baseline"] = cpu_baseline(sample_steps=1)
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -654,6 +712,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = rc 100 per GPU (rc = 100 N step circuit); strong = ONE rc = 100 fold, its key split N ways")
     ap.add_argument("--latency-sms", type=int, default=0, help="SM partition (green contexts): SMs reserved for the chain's latency-shaped kernels")
+    ap.add_argument("--workload", default="fib", choices=["fib", "sha256_ivc", "trie_nivc"],
+                    help="fib = the BASELINE metric (benches/fibonacci.rs rc=100); sha256_ivc / trie_nivc = BASELINE configs[3] / configs[4] shapes")
+    ap.add_argument("--rc", type=int, default=None, help="frames per step (default: 100 fib, 10 sha256_ivc, 400 trie_nivc)")
     ap.add_argument("--live-slots", type=float, default=LIVE_SLOT_FRACTION,
                     help="fraction of a frame's slots with a non-dummy preimage (dummy slots share one witness, multiframe.rs:553-577)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

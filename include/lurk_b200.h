@@ -120,6 +120,17 @@ typedef struct lurk_dag_node {
 } lurk_dag_node;
 int lurk_dag_hash(int field_id, const lurk_dag_node *nodes, size_t n, const uint8_t *atom_digests,
                   size_t n_atoms, uint8_t *out_digests);
+/* Routing aid, host only (works without a GPU): shape of the dependency DAG and a cost estimate.  A level costs one
+ * dependent Poseidon latency on the GPU whatever its width, so deep and narrow stores (lists hashed cons by cons) are
+ * faster on the caller's own CPU path (hash_ptr_val_unsafe, src/lem/store_core.rs:199-248), wide ones on the GPU.  The
+ * library never hashes on the CPU itself: use_gpu == 0 means "keep this hydration on the reference's CPU path". */
+typedef struct lurk_dag_plan {
+    uint64_t nodes, levels, max_width;
+    uint64_t est_gpu_us;       /* levels * ~170 us + nodes / 23 M/s + transfers */
+    uint64_t est_cpu_core_us;  /* nodes * ~50 us on one core */
+    int use_gpu;               /* est_gpu_us < the level-parallel CPU estimate on 8 cores */
+} lurk_dag_plan;
+int lurk_dag_hash_plan(const lurk_dag_node *nodes, size_t n, size_t n_atoms, lurk_dag_plan *plan);
 
 /* ---------------------------------------------------------------------------------------------------
  * S4  Pedersen commitment = multi-scalar multiplication.  Replaces Arecibo

@@ -22,6 +22,11 @@ class DagNode(C.Structure):
     _fields_ = [("kind", C.c_uint8), ("reserved", C.c_uint8), ("tag", C.c_uint16 * 4), ("child", C.c_uint32 * 4)]
 
 
+class DagPlan(C.Structure):
+    _fields_ = [("nodes", C.c_uint64), ("levels", C.c_uint64), ("max_width", C.c_uint64), ("est_gpu_us", C.c_uint64),
+                ("est_cpu_core_us", C.c_uint64), ("use_gpu", C.c_int)]
+
+
 class FoldConfig(C.Structure):
     _fields_ = [("curve_id", C.c_int), ("depth", C.c_int), ("n_w", C.c_uint64), ("n_x", C.c_uint64), ("n_rows", C.c_uint64),
                 ("row_ptr", C.c_void_p * 3), ("col", C.c_void_p * 3), ("val", C.c_void_p * 3), ("fmt", C.c_int),
@@ -61,6 +66,7 @@ PROTOTYPES = {
     "lurk_bitdecomp_witness_batch": (_i, [_i, _vp, _sz, _vp, _i]),
     "lurk_bitdecomp_witness_batch_dev": (_i, [_i, _vp, _sz, _vp, _i, _vp]),
     "lurk_dag_hash": (_i, [_i, _vp, _sz, _vp, _sz, _vp]),
+    "lurk_dag_hash_plan": (_i, [_vp, _sz, _sz, C.POINTER(DagPlan)]),
     "lurk_msm_ctx_create": (_i, [_i, _vp, _sz, _i, C.POINTER(_vp)]),
     "lurk_msm_ctx_create_dev": (_i, [_i, _vp, _sz, C.POINTER(_vp)]),
     "lurk_msm_ctx_destroy": (None, [_vp]),

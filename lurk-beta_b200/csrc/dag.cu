@@ -9,6 +9,7 @@
 #include "poseidon_api.h"
 
 #include <algorithm>
+#include <cstring>
 
 namespace lurk {
 
@@ -66,12 +67,11 @@ static int kind_children(int kind) {
     return 0;
 }
 
-template <class F>
-static int dag_hash(const lurk_dag_node *nodes, size_t n, const uint8_t *atoms, size_t n_atoms, uint8_t *out) {
+// host pass shared by the hash and the plan: height of every node (children first), LURK_ERR_* on malformed input
+static int dag_heights(const lurk_dag_node *nodes, size_t n, size_t n_atoms, std::vector<uint32_t> &height, uint32_t *max_h) {
     if (n + n_atoms >= 0xffffffffull) { set_error("DAG too large"); return LURK_ERR_ARG; }
-    // ---- host: heights and (height, arity) batches
-    std::vector<uint32_t> height(n);
-    uint32_t max_h = 0;
+    height.resize(n);
+    uint32_t mh = 0;
     for (size_t i = 0; i < n; i++) {
         const int nch = kind_children(nodes[i].kind);
         if (!nch) { set_error("node %zu: unknown kind %d", i, (int)nodes[i].kind); return LURK_ERR_ARG; }
@@ -84,8 +84,41 @@ static int dag_hash(const lurk_dag_node *nodes, size_t n, const uint8_t *atoms, 
             h = std::max(h, height[ix] + 1);
         }
         height[i] = h;
-        max_h = std::max(max_h, h);
+        mh = std::max(mh, h);
     }
+    *max_h = mh;
+    return LURK_OK;
+}
+
+// per-thread stream + stream-ordered scratch: concurrent hydrations from rayon workers neither serialise on the legacy
+// default stream nor synchronise the device with cudaMalloc / cudaFree
+struct DagStream {
+    cudaStream_t s = nullptr;
+    int device = -1;
+    ~DagStream() { if (s) cudaStreamDestroy(s); }
+    int get(cudaStream_t *out) {
+        int dev = 0;
+        LURK_CUDA_TRY(cudaGetDevice(&dev));
+        if (s && dev != device) { cudaStreamDestroy(s); s = nullptr; }
+        if (!s) { LURK_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); device = dev; }
+        *out = s;
+        return LURK_OK;
+    }
+};
+struct AsyncBuf {
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    ~AsyncBuf() { if (p) cudaFreeAsync(p, s); }
+    int alloc(size_t bytes, cudaStream_t st) { s = st; LURK_CUDA_TRY(cudaMallocAsync(&p, bytes ? bytes : 16, st)); return LURK_OK; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+template <class F>
+static int dag_hash(const lurk_dag_node *nodes, size_t n, const uint8_t *atoms, size_t n_atoms, uint8_t *out) {
+    // ---- host: heights and (height, arity) batches
+    std::vector<uint32_t> height;
+    uint32_t max_h = 0;
+    LURK_TRY(dag_heights(nodes, n, n_atoms, height, &max_h));
     static const int ARITIES[4] = {3, 4, 6, 8};
     auto slot = [&](size_t i) { int a = kind_arity(nodes[i].kind); return (size_t)height[i] * 4 + (a == 3 ? 0 : a == 4 ? 1 : a == 6 ? 2 : 3); };
     std::vector<uint32_t> start(((size_t)max_h + 1) * 4 + 1, 0);
@@ -97,35 +130,40 @@ static int dag_hash(const lurk_dag_node *nodes, size_t n, const uint8_t *atoms, 
     for (size_t k = 0; k + 1 < start.size(); k++) max_batch = std::max<size_t>(max_batch, start[k + 1] - start[k]);
 
     // ---- device
-    DevBuf d_nodes, d_order, d_table, d_pre, d_dig;
-    LURK_TRY(d_nodes.alloc(n * sizeof(lurk_dag_node)));
-    LURK_TRY(d_order.alloc(n * sizeof(uint32_t)));
-    LURK_TRY(d_table.alloc((n_atoms + n) * sizeof(F)));
-    LURK_TRY(d_pre.alloc(max_batch * 8 * sizeof(F)));
-    LURK_TRY(d_dig.alloc(max_batch * sizeof(F)));
-    LURK_CUDA_TRY(cudaMemcpy(d_nodes.p, nodes, d_nodes.bytes, cudaMemcpyHostToDevice));
-    LURK_CUDA_TRY(cudaMemcpy(d_order.p, order.data(), d_order.bytes, cudaMemcpyHostToDevice));
+    static thread_local DagStream tls;
+    cudaStream_t st = nullptr;
+    LURK_TRY(tls.get(&st));
+    AsyncBuf d_nodes, d_order, d_table, d_pre, d_dig;
+    LURK_TRY(d_nodes.alloc(n * sizeof(lurk_dag_node), st));
+    LURK_TRY(d_order.alloc(n * sizeof(uint32_t), st));
+    LURK_TRY(d_table.alloc((n_atoms + n) * sizeof(F), st));
+    LURK_TRY(d_pre.alloc(max_batch * 8 * sizeof(F), st));
+    LURK_TRY(d_dig.alloc(max_batch * sizeof(F), st));
+    LURK_CUDA_TRY(cudaMemcpyAsync(d_nodes.p, nodes, n * sizeof(lurk_dag_node), cudaMemcpyHostToDevice, st));
+    LURK_CUDA_TRY(cudaMemcpyAsync(d_order.p, order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     if (n_atoms) {
-        LURK_CUDA_TRY(cudaMemcpy(d_table.p, atoms, n_atoms * sizeof(F), cudaMemcpyHostToDevice));
+        LURK_CUDA_TRY(cudaMemcpyAsync(d_table.p, atoms, n_atoms * sizeof(F), cudaMemcpyHostToDevice, st));
         int bad = 0;
-        LURK_TRY(check_reduced_dev<F>(d_table.p, n_atoms, 0, &bad));
+        LURK_TRY(check_reduced_dev<F>(d_table.p, n_atoms, st, &bad));
         if (bad) { set_error("%d atom digest(s) are not reduced below the field modulus", bad); return LURK_ERR_RANGE; }
-        LURK_TRY(convert_dev<F>(d_table.p, n_atoms, LURK_FMT_MONTGOMERY, d_table.p, 0));
+        LURK_TRY(convert_dev<F>(d_table.p, n_atoms, LURK_FMT_MONTGOMERY, d_table.p, st));
     }
     for (uint32_t h = 0; h <= max_h; h++) {
         for (int a = 0; a < 4; a++) {
             const uint32_t b0 = start[(size_t)h * 4 + a], cnt = start[(size_t)h * 4 + a + 1] - b0;
             if (!cnt) continue;
             const uint32_t *batch = d_order.as<uint32_t>() + b0;
-            dag_gather_kernel<F><<<(cnt + 127) / 128, 128>>>(d_nodes.as<lurk_dag_node>(), batch, cnt, ARITIES[a], d_table.as<F>(), d_pre.as<F>());
-            LURK_TRY((launch_poseidon<F, false>(ARITIES[a], d_pre.p, cnt, d_dig.p, LURK_FMT_MONTGOMERY, LURK_FMT_MONTGOMERY, 0)));
-            dag_scatter_kernel<F><<<(cnt + 127) / 128, 128>>>(d_dig.as<F>(), batch, cnt, (uint32_t)n_atoms, d_table.as<F>());
+            dag_gather_kernel<F><<<(cnt + 127) / 128, 128, 0, st>>>(d_nodes.as<lurk_dag_node>(), batch, cnt, ARITIES[a], d_table.as<F>(), d_pre.as<F>());
+            LURK_CUDA_TRY(cudaGetLastError());
+            LURK_TRY((launch_poseidon<F, false>(ARITIES[a], d_pre.p, cnt, d_dig.p, LURK_FMT_MONTGOMERY, LURK_FMT_MONTGOMERY, st)));
+            dag_scatter_kernel<F><<<(cnt + 127) / 128, 128, 0, st>>>(d_dig.as<F>(), batch, cnt, (uint32_t)n_atoms, d_table.as<F>());
+            LURK_CUDA_TRY(cudaGetLastError());
         }
     }
-    LURK_CUDA_TRY(cudaGetLastError());
     F *node_table = d_table.as<F>() + n_atoms;
-    LURK_TRY(convert_dev<F>(node_table, n, LURK_FMT_CANONICAL, node_table, 0));
-    LURK_CUDA_TRY(cudaMemcpy(out, node_table, n * sizeof(F), cudaMemcpyDeviceToHost));
+    LURK_TRY(convert_dev<F>(node_table, n, LURK_FMT_CANONICAL, node_table, st));
+    LURK_CUDA_TRY(cudaMemcpyAsync(out, node_table, n * sizeof(F), cudaMemcpyDeviceToHost, st));
+    LURK_CUDA_TRY(cudaStreamSynchronize(st));
     return LURK_OK;
 }
 
@@ -139,4 +177,31 @@ extern "C" int lurk_dag_hash(int field_id, const lurk_dag_node *nodes, size_t n,
     if (n == 0) return LURK_OK;
     if (!nodes || !out_digests || (n_atoms && !atom_digests)) { set_error("null argument"); return LURK_ERR_ARG; }
     return dispatch_field(field_id, [&](auto f) { return dag_hash<decltype(f)>(nodes, n, atom_digests, n_atoms, out_digests); });
+}
+
+// Routing aid for the caller (StoreCore::hydrate_z_cache, src/lem/store_core.rs:256-269): a level of the DAG costs one
+// dependent Poseidon latency on the GPU (~170 us: three launches + one warp-per-sponge hash) whatever its width, a CPU core
+// hashes ~20 k nodes/s, and the wide-DAG GPU rate is ~23 M nodes/s (profiles/r1_ncu_summary.md).  The library never hashes on
+// the CPU itself; it tells the caller when its own CPU path is the better choice (deep, narrow stores).
+extern "C" int lurk_dag_hash_plan(const lurk_dag_node *nodes, size_t n, size_t n_atoms, lurk_dag_plan *plan) {
+    if (!plan || (n && !nodes)) { set_error("null argument"); return LURK_ERR_ARG; }
+    memset(plan, 0, sizeof *plan);
+    if (n == 0) return LURK_OK;
+    std::vector<uint32_t> height;
+    uint32_t max_h = 0;
+    LURK_TRY(dag_heights(nodes, n, n_atoms, height, &max_h));
+    std::vector<uint32_t> width((size_t)max_h + 1, 0);
+    for (size_t i = 0; i < n; i++) width[height[i]]++;
+    plan->nodes = n;
+    plan->levels = (uint64_t)max_h + 1;
+    plan->max_width = *std::max_element(width.begin(), width.end());
+    const double gpu_us = 150.0 + plan->levels * 170.0 + (double)n / 23.0 + (double)(n * 60) / 25000.0;   // launch chain + throughput + PCIe
+    const double cpu_core_us = (double)n * 50.0;
+    plan->est_gpu_us = (uint64_t)gpu_us;
+    plan->est_cpu_core_us = (uint64_t)cpu_core_us;
+    // the CPU side parallelises over a level too (rayon): assume 8 cores on levels wider than 8 nodes
+    double cpu_us = 0;
+    for (uint32_t w : width) cpu_us += 50.0 * ((w + 7) / 8);
+    plan->use_gpu = gpu_us < cpu_us ? 1 : 0;
+    return LURK_OK;
 }

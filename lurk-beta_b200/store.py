@@ -73,10 +73,8 @@ class StoreCore:
                 stack.append((c, False))
         return order
 
-    def _hash_vals(self, vals):
-        """digest table handed to the library: [atoms | digests of already-hashed compound children | vals]"""
-        if not vals:
-            return
+    def _build_nodes(self, vals):
+        """node list + digest table handed to the library: [atoms | digests of already-hashed compound children | vals]"""
         n_atoms = len(self._atoms)
         slot = {v: i for i, v in enumerate(vals)}
         extra, extra_ix = [], {}
@@ -99,13 +97,29 @@ class StoreCore:
                     nodes[i]["child"][j] = base + slot[c]
                 else:
                     nodes[i]["child"][j] = n_atoms + extra_ix[self.z_cache[c]]
-        atoms = pack(self._atoms + extra)
+        return nodes, pack(self._atoms + extra), base
+
+    def _hash_vals(self, vals):
+        if not vals:
+            return
+        nodes, atoms, base = self._build_nodes(vals)
         out = np.zeros(len(vals) * 32, dtype=np.uint8)
         _capi.check(_capi.lib().lurk_dag_hash(self.field_id, _capi.np_ptr(nodes), len(vals), _capi.np_ptr(atoms),
                                               base, _capi.np_ptr(out)))
         for v, d in zip(vals, unpack(out)):
             self.z_cache[v] = d
             self.inverse_z_cache[d] = v
+
+    def hydration_plan(self):
+        """lurk_dag_hash_plan for the queued nodes (host only).  The caller -- the reference's StoreCore -- keeps deep,
+        narrow hydrations on its own CPU path (hash_ptr_val_unsafe, store_core.rs:199-248) when `use_gpu` is 0."""
+        import ctypes as C
+        todo = [v for v in self.dehydrated if v not in self.z_cache]
+        plan = _capi.DagPlan()
+        if todo:
+            nodes, _atoms, base = self._build_nodes(todo)
+            _capi.check(_capi.lib().lurk_dag_hash_plan(_capi.np_ptr(nodes), len(todo), base, C.byref(plan)))
+        return plan
 
     def hydrate_z_cache(self):
         """hash every queued compound node (store_core.rs:266-269)"""

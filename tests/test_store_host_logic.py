@@ -206,3 +206,29 @@ def test_chained_commitment_goldens_through_store_flattening(HL):
     expr = e.lst([e.lst([e.sym("lurk", "open"), e.num(c0)]), e.num(9)])
     out = e.cons(e.num(9), s.intern_atom(COMM, c1))
     assert s.hide(0, e.claim(expr, e.env0, out, e.env0)) == GOLDEN["G21"]
+
+
+def test_hydration_plan_routes_chains_to_the_cpu_and_wide_dags_to_the_gpu(L):
+    """lurk_dag_hash_plan (host only): a 2000-deep cons chain is one dependent hash per level -- slower on the GPU than one
+    CPU core (profiles/r1_ncu_summary.md: 337 ms vs ~100 ms) -- so the plan keeps it on the caller's CPU path; a wide store
+    goes to the GPU.  Malformed input is rejected as by lurk_dag_hash."""
+    import ctypes as C
+    import numpy as np
+    from lurk_beta_b200 import _capi
+    lib = _capi.lib()
+    node_t = np.dtype([("kind", "u1"), ("reserved", "u1"), ("tag", "<u2", (4,)), ("child", "<u4", (4,))], align=True)
+    n_atoms = 16
+    chain = np.zeros(2000, dtype=node_t)
+    chain["kind"] = 2
+    chain["child"][:, 0] = np.maximum(n_atoms + np.arange(2000) - 1, 0)
+    chain["child"][0, 0] = 0
+    plan = _capi.DagPlan()
+    _capi.check(lib.lurk_dag_hash_plan(_capi.np_ptr(chain), 2000, n_atoms, C.byref(plan)))
+    assert (plan.nodes, plan.levels, plan.max_width, plan.use_gpu) == (2000, 2000, 1, 0)
+    wide = np.zeros(1 << 16, dtype=node_t)
+    wide["kind"] = 4
+    wide["child"] = np.random.default_rng(0).integers(0, n_atoms, size=(1 << 16, 4))
+    _capi.check(lib.lurk_dag_hash_plan(_capi.np_ptr(wide), 1 << 16, n_atoms, C.byref(plan)))
+    assert (plan.levels, plan.max_width, plan.use_gpu) == (1, 1 << 16, 1)
+    chain["child"][5, 0] = n_atoms + 9                      # forward reference
+    assert lib.lurk_dag_hash_plan(_capi.np_ptr(chain), 2000, n_atoms, C.byref(plan)) == _capi.ERR_ORDER

@@ -12,7 +12,7 @@ import bench
 
 if len(sys.argv) > 1:
     bench.LIVE_SLOT_FRACTION = float(sys.argv[1])
-wl = bench.FoldStepGPU(0, 1, latency_sms=int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+wl = bench.FoldStepGPU(0, 1, latency_sms=int(sys.argv[2]) if len(sys.argv) > 2 else 0, workload=sys.argv[3] if len(sys.argv) > 3 else "fib")
 wl.start(True)
 for _ in range(4):
     wl.step(False)
