@@ -469,7 +469,7 @@ def verify_full_size(wl, rank):
 def ncu_traffic():
     """dram bytes per launch of the dominant kernel from this round's committed ncu --set full capture (profiles/), or None"""
     import csv
-    path = os.path.join(ROOT, "profiles", "r2_ncu_full_msm_accumulate_raw.csv")
+    path = os.path.join(ROOT, "profiles", "r2_ncu_full_msm_accumulate_iso_raw.csv")
     try:
         rows = list(csv.reader(open(path)))
         hdr = rows[0]
@@ -584,8 +584,9 @@ def run_gpu(args):
             "roofline": {"kernel": "msm_accumulate_kernel (bucket accumulation of commit(T) / commit(W))", "bound": "hbm",
                          "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
                          "traffic": ncu_traffic(),
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch in profiles/r2_ncu_full_msm_accumulate_raw.csv (ncu --set full of "
-                                         "this kernel at this size); Pippenger gathers each 64-byte window multiple once per window (13 x 64 B + index per term)",
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch in profiles/r2_ncu_full_msm_accumulate_iso_raw.csv (ncu --set full of "
+                                         "this kernel on the same dense 1114100-term vector and c = 20 table, tools/acc_iso.py); Pippenger gathers each 64-byte "
+                                         "window multiple once per window (13 x 64 B + index per term)",
                          "avg_launch_ms": round(iso_ms, 4), "avg_launch_ms_overlapped_in_step": {"commit_W": round(st["accumulate_w_ms"], 4),
                                                                                                 "commit_T": round(st["accumulate_t_ms"], 4)},
                          "algorithmic_bytes_per_launch": int(terms * 96),
