@@ -372,7 +372,8 @@ class FoldStepGPU:
             self.inst.append(Instance(torch, L, CURVE, TRIE_LOOKUP, 1, ck, ck, 1, 0, seed + 5, 1.0, mk_x()))
         # the secondary circuit of the cycle (Grumpkin): whole witness from the host, replicated on every rank
         self.ck2 = L.CommitmentKey(CURVE2, L.synthetic_bases(CURVE2, 1 << 14, fmt=M), fmt=M)
-        self.inst.append(Instance(torch, L, CURVE2, SECONDARY, 1, self.ck2, self.ck2, 1, 0, seed + 7, 1.0, mk_x()))
+        if not os.environ.get("LURK_BENCH_NO_SECONDARY"):        # measurement aid (the chain of the primary circuit alone)
+            self.inst.append(Instance(torch, L, CURVE2, SECONDARY, 1, self.ck2, self.ck2, 1, 0, seed + 7, 1.0, mk_x()))
         self.ctx = self.inst[0].ctx
         self.nW, self.nT, self.X2 = self.inst[0].nW, self.inst[0].nT, self.inst[0].x2
         self.h2d_bytes = sum(i.h2d_bytes for i in self.inst)

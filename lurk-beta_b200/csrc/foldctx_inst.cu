@@ -211,13 +211,28 @@ struct FoldCtx final : FoldCtxBase {
         }
         LURK_TRY(lurk_msm_ctx_clone(ck_t, &ckChk));
         LURK_TRY(lurk_msm_ctx_clone(ck_w, &ckChkW));     // check_running must not touch a prefetched commit(W2)
+        {
+            static const int w_pad_kb = [] { const char *e = getenv("LURK_FOLD_W_SMEM_KB"); return e ? atoi(e) : FOLD_W_SMEM_KB; }();   // tuning aid
+            for (int b = 0; b < D; b++) ckW[b]->acc_smem_pad = (unsigned)w_pad_kb * 1024u;
+        }
         for (int b = 0; b < D; b++) lurk_msm_ctx_set_profiling(ckW[b], 1);
         lurk_msm_ctx_set_profiling(ckT, 1);
 
         // streams: the chain gets the high priority; optional SM partition
         int lo = 0, hi = 0;
         LURK_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        if (c.latency_sms > 0) {
+        static const bool stage_a_partition = getenv("LURK_FOLD_PARTITION_STAGE_A") != nullptr;   // experiment: see profiles/r2_ncu_summary.md
+        if (c.latency_sms > 0 && stage_a_partition) {
+            // the other split: `latency_sms` SMs for ALL of stage A (slot witnesses, commit(W), A z2..), the rest for the chain
+            cudaStream_t small[4] = {nullptr, nullptr, nullptr, nullptr}, big_lo[1] = {nullptr};
+            if (green_streams(c.latency_sms, small, 4, &sB, big_lo, 1) != LURK_OK) {
+                set_error("SM partitioning (green contexts) is not available on this driver");
+                return LURK_ERR_CUDA;
+            }
+            sK[0] = small[0]; sK[1] = small[1]; sK[2] = small[2]; sA = small[3];
+            sC = big_lo[0];
+            sT = sB;
+        } else if (c.latency_sms > 0) {
             cudaStream_t tiny[2] = {nullptr, nullptr}, big_lo[4] = {nullptr, nullptr, nullptr, nullptr};
             if (green_streams(c.latency_sms, tiny, 2, &sB, big_lo, 4) != LURK_OK) {
                 set_error("SM partitioning (green contexts) is not available on this driver");
@@ -566,6 +581,9 @@ struct FoldCtx final : FoldCtxBase {
         if (fmt != LURK_FMT_CANONICAL && fmt != LURK_FMT_MONTGOMERY) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
         if (b_pending[b]) { set_error("buffer %d: the previous step's result has not been collected", b); return LURK_ERR_ARG; }
         const bool staged = !(flags & FOLD_INPUTS_RESIDENT);
+        // measurement aid: with resident inputs, re-use the fresh instance already prepared in this buffer (the chain alone)
+        static const bool skip_a = getenv("LURK_FOLD_SKIP_STAGE_A") != nullptr;
+        if (skip_a && !staged && a_recorded[b]) return LURK_OK;
         if (!staged && fmt != LURK_FMT_MONTGOMERY) { set_error("device-resident inputs are Montgomery form"); return LURK_ERR_ARG; }
         Fs *W2 = z2[b].as<Fs>();
         unsigned k = 0;
