@@ -231,7 +231,8 @@ __device__ __forceinline__ void store_xyzz(XYZZ<Fb> *p, const XYZZ<Fb> &a) {
 // level 1: fixed-length segments of the sorted list
 // MINB = resident CTAs per SM the register allocation is held to: 4 (126 registers, no spills) is best while the key is
 // L2 resident; the fixed-base table (1.7 GB, DRAM gathers) gains ~5 % from 5 CTAs (96 registers, ~150 B of spills).
-template <class Fb, int MINB>
+// DIRECT: the list is already a list of affine points (the output of the pair rounds below): entry `pos` is bases[pos], no sign
+template <class Fb, int MINB, bool DIRECT = false>
 __global__ void __launch_bounds__(128, MINB) msm_accumulate_kernel(const uint32_t *__restrict__ offsets, uint32_t nbuckets,
                                                              const uint32_t *__restrict__ sorted, const Affine<Fb> *__restrict__ bases,
                                                              XYZZ<Fb> *__restrict__ bucket_acc, uint32_t *__restrict__ pkey,
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate_kernel(const uint32_
     uint32_t key = lo;
     uint32_t run_end = min(offsets[key + 1], end);
     bool first_run = true;
-    uint32_t e_next = sorted[start];
+    uint32_t e_next = DIRECT ? start : sorted[start];
     Affine<Fb> p_next = load_affine(bases + (e_next & 0x7fffffffu));
     XYZZ<Fb> acc = XYZZ<Fb>::identity();
     // ONE flat loop over the segment: every lane performs exactly one addition per iteration, so lanes whose bucket
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate_kernel(const uint32_
         const Affine<Fb> p = p_next;
         pos++;
         if (pos < end) {   // prefetch the next entry while this addition runs
-            e_next = sorted[pos];
+            e_next = DIRECT ? pos : sorted[pos];
             p_next = load_affine(bases + (e_next & 0x7fffffffu));
         }
         acc.add_affine(p, (e >> 31) != 0);
@@ -277,6 +278,158 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate_kernel(const uint32_
                 run_end = min(offsets[key + 1], end);
             }
         }
+    }
+}
+
+// ---- pair rounds: batched-affine additions in front of the XYZZ accumulation ------------------------------------------------
+// A mixed XYZZ addition costs 10 field products; an AFFINE addition costs 3 (lambda = dy / dx; x3 = lambda^2 - x1 - x2;
+// y3 = lambda (x1 - x3) - y1) plus one inversion -- and inversions batch: Montgomery's trick turns the inversions of a whole CTA
+// (128 threads x PAIR_B additions) into ONE inversion (binary GCD, on the ALU pipe, by one thread) + 3 products per addition + a
+// dozen products per thread for the cross-thread prefix / suffix products.  ~7 products per addition instead of 10.
+// Independent additions come from the sorted list itself: inside every bucket's run, entries 2j and 2j + 1 are added pairwise (an odd
+// tail is copied), which halves every run: out run k has ceil(m_k / 2) affine points.  One or two such rounds (half resp. three
+// quarters of all additions) run before the fixed-length-segment XYZZ accumulation takes the rest.
+static constexpr int PAIR_B = 16;        // output points per thread and batch
+
+static __global__ void __launch_bounds__(256) msm_halve_kernel(const uint32_t *__restrict__ offs_in, uint32_t nbuckets, uint32_t *__restrict__ counts_out) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k <= nbuckets; k += gridDim.x * blockDim.x)
+        counts_out[k] = k < nbuckets ? (offs_in[k + 1] - offs_in[k] + 1u) >> 1 : 0u;
+}
+
+// the two inputs of output slot q of bucket k and how they combine
+template <class Fb>
+struct PairIn {
+    Affine<Fb> p1, p2;
+    int kind;            // 0 copy p1, 1 chord addition, 2 doubling of p1, 3 result is the identity
+};
+template <class Fb, bool FIRST>
+__device__ __forceinline__ Affine<Fb> pair_load(const uint32_t *__restrict__ sorted, const Affine<Fb> *__restrict__ pts, uint32_t pos) {
+    if (!FIRST) return load_affine(pts + pos);
+    const uint32_t e = sorted[pos];
+    Affine<Fb> p = load_affine(pts + (e & 0x7fffffffu));
+    if (e >> 31) p.y = p.y.neg();
+    return p;
+}
+template <class Fb, bool FIRST>
+__device__ __forceinline__ PairIn<Fb> pair_fetch(const uint32_t *__restrict__ sorted, const Affine<Fb> *__restrict__ pts, uint32_t in, uint32_t run_end) {
+    PairIn<Fb> r;
+    r.p1 = pair_load<Fb, FIRST>(sorted, pts, in);
+    r.kind = 0;
+    r.p2 = r.p1;
+    if (in + 1 < run_end) {
+        r.p2 = pair_load<Fb, FIRST>(sorted, pts, in + 1);
+        if (r.p1.is_identity()) { r.p1 = r.p2; }                       // 0 + Q: copy Q
+        else if (r.p2.is_identity()) {}                                  // P + 0: copy P
+        else if (r.p1.x == r.p2.x) r.kind = (r.p1.y == r.p2.y && !r.p1.y.is_zero()) ? 2 : 3;
+        else r.kind = 1;
+    }
+    return r;
+}
+template <class Fb>
+__device__ __forceinline__ Fb pair_denominator(const PairIn<Fb> &in) {
+    if (in.kind == 1) return in.p2.x - in.p1.x;
+    if (in.kind == 2) return in.p1.y.dbl();
+    return Fb::one();
+}
+
+// 1 / v for every thread of a 128-thread CTA with ONE field inversion (v != 0 everywhere)
+template <class Fb>
+__device__ __forceinline__ Fb block_batch_inverse(const Fb &v) {
+    __shared__ Fb warp_tot[4];
+    __shared__ Fb warp_inv[4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    Fb pre = v, suf = v;                       // inclusive prefix / suffix products inside the warp
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        Fb a, b;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { a.v[i] = __shfl_up_sync(0xffffffffu, pre.v[i], d); b.v[i] = __shfl_down_sync(0xffffffffu, suf.v[i], d); }
+        if (lane >= d) pre = pre * a;
+        if (lane + d < 32) suf = suf * b;
+    }
+    if (lane == 31) warp_tot[w] = pre;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const Fb t0 = warp_tot[0], t1 = warp_tot[1], t2 = warp_tot[2], t3 = warp_tot[3];
+        const Fb t01 = t0 * t1, t23 = t2 * t3;
+        const Fb inv = (t01 * t23).inv_vartime();
+        const Fb i01 = inv * t23, i23 = inv * t01;        // 1 / (t0 t1), 1 / (t2 t3)
+        warp_inv[0] = i01 * t1; warp_inv[1] = i01 * t0; warp_inv[2] = i23 * t3; warp_inv[3] = i23 * t2;
+    }
+    __syncthreads();
+    Fb ep, es;                                  // exclusive prefix / suffix
+#pragma unroll
+    for (int i = 0; i < 8; i++) { ep.v[i] = __shfl_up_sync(0xffffffffu, pre.v[i], 1); es.v[i] = __shfl_down_sync(0xffffffffu, suf.v[i], 1); }
+    Fb r = warp_inv[w];
+    if (lane > 0) r = r * ep;
+    if (lane < 31) r = r * es;
+    __syncthreads();                            // the shared arrays are reused by the next batch
+    return r;
+}
+
+// One pair round.  offs_in / offs_out: bucket offsets of the input / output lists (offs_out = scan of ceil(m / 2)).
+// Thread t produces output slots [t * PAIR_B, (t + 1) * PAIR_B).
+template <class Fb, bool FIRST>
+__global__ void __launch_bounds__(128) msm_pair_kernel(const uint32_t *__restrict__ offs_in, const uint32_t *__restrict__ offs_out, uint32_t nbuckets,
+                                                       const uint32_t *__restrict__ sorted, const Affine<Fb> *__restrict__ pts_in,
+                                                       Affine<Fb> *__restrict__ pts_out) {
+    extern __shared__ __align__(16) unsigned char pair_smem[];
+    uint4 *pp = reinterpret_cast<uint4 *>(pair_smem);            // prefix products [j][half][thread]
+    const uint32_t total = offs_out[nbuckets];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t start64 = ((uint64_t)blockIdx.x * blockDim.x + tid) * PAIR_B;
+    if ((uint64_t)blockIdx.x * blockDim.x * PAIR_B >= total) return;          // the whole CTA is past the end
+    const bool active = start64 < total;
+    const uint32_t start = active ? (uint32_t)start64 : 0, end = active ? (uint32_t)min((uint64_t)total, start64 + PAIR_B) : 0;
+    uint32_t k0 = 0;
+    if (active) {
+        uint32_t lo = 0, hi = nbuckets;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (offs_out[mid] <= start) lo = mid; else hi = mid; }
+        k0 = lo;
+    }
+    auto put = [&](int j, const Fb &x) {
+        pp[(j * 2 + 0) * 128 + tid] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+        pp[(j * 2 + 1) * 128 + tid] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+    };
+    auto get = [&](int j) {
+        const uint4 a = pp[(j * 2 + 0) * 128 + tid], b = pp[(j * 2 + 1) * 128 + tid];
+        Fb x;
+        x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w; x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
+        return x;
+    };
+    // pass 1: running product of the denominators
+    Fb run = Fb::one();
+    uint32_t k = k0;
+    for (uint32_t q = start; q < end; q++) {
+        while (offs_out[k + 1] <= q) k++;
+        const uint32_t in = offs_in[k] + 2 * (q - offs_out[k]);
+        const PairIn<Fb> pi = pair_fetch<Fb, FIRST>(sorted, pts_in, in, offs_in[k + 1]);
+        run = run * pair_denominator(pi);
+        put((int)(q - start), run);
+    }
+    Fb inv = block_batch_inverse(run);          // 1 / (product of this thread's denominators)
+    // pass 2, backwards: peel one denominator at a time
+    for (uint32_t q = end; q-- > start;) {
+        while (offs_out[k] > q) k--;
+        const uint32_t in = offs_in[k] + 2 * (q - offs_out[k]);
+        const PairIn<Fb> pi = pair_fetch<Fb, FIRST>(sorted, pts_in, in, offs_in[k + 1]);
+        const int j = (int)(q - start);
+        const Fb den = pair_denominator(pi);
+        const Fb inv_d = j ? inv * get(j - 1) : inv;     // 1 / den
+        inv = inv * den;
+        Affine<Fb> o = pi.p1;
+        if (pi.kind == 3) { o.x = Fb::zero(); o.y = Fb::zero(); }
+        else if (pi.kind) {
+            Fb num;
+            if (pi.kind == 1) num = pi.p2.y - pi.p1.y;
+            else { const Fb xx = pi.p1.x.sqr(); num = xx.dbl() + xx; }
+            const Fb lam = num * inv_d;
+            const Fb x3 = lam.sqr() - pi.p1.x - pi.p2.x;
+            o.y = lam * (pi.p1.x - x3) - pi.p1.y;
+            o.x = x3;
+        }
+        store_fe(&pts_out[q].x, o.x);
+        store_fe(&pts_out[q].y, o.y);
     }
 }
 
@@ -524,7 +677,7 @@ __global__ void __launch_bounds__(256) msm_bases_to_mont_kernel(Fb *coords, size
 
 // ----------------------------------------------------------------------------- context
 struct MsmScratch {
-    DevBuf counts, offsets, tiles, sorted, buckets, pkey[2], ppt[2], chunks, chunk_sums, slices, wins, result, scalars;
+    DevBuf counts, offsets, tiles, sorted, buckets, pkey[2], ppt[2], chunks, chunk_sums, slices, wins, result, scalars, pair_offs[2], pair_pts[2];
     void *h_wins = nullptr;   // pinned
     void *h_stage[2] = {nullptr, nullptr};          // pinned staging for host-buffer scalars
     cudaEvent_t stage_done[2] = {nullptr, nullptr};
@@ -669,30 +822,69 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
     msm_scan_apply_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_offsets, ntiles, offsets);
     msm_scatter_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, sub, n, fmt, P.c, P.nwin, key_stride, base_stride, offsets, cursor, sorted);
     const unsigned pad = ctx->acc_smem_pad;
-    if (pad) {
-        static std::mutex pad_mu;
-        static std::vector<int> pad_done;
+    {
+        // one-off per device: opt-ins for dynamic shared memory (the pair kernels' prefix products; the optional occupancy pad)
+        static std::mutex attr_mu;
+        static std::vector<int> attr_done;
         int dev = 0;
         LURK_CUDA_TRY(cudaGetDevice(&dev));
-        std::lock_guard<std::mutex> g(pad_mu);
-        if (std::find(pad_done.begin(), pad_done.end(), dev) == pad_done.end()) {
-            LURK_CUDA_TRY(cudaFuncSetAttribute(msm_accumulate_kernel<Fb, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            LURK_CUDA_TRY(cudaFuncSetAttribute(msm_accumulate_kernel<Fb, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            pad_done.push_back(dev);
+        std::lock_guard<std::mutex> g(attr_mu);
+        if (std::find(attr_done.begin(), attr_done.end(), dev) == attr_done.end()) {
+            LURK_CUDA_TRY(cudaFuncSetAttribute(msm_accumulate_kernel<Fb, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            LURK_CUDA_TRY(cudaFuncSetAttribute(msm_accumulate_kernel<Fb, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            LURK_CUDA_TRY(cudaFuncSetAttribute(msm_accumulate_kernel<Fb, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            LURK_CUDA_TRY(cudaFuncSetAttribute(msm_pair_kernel<Fb, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_B * 4096));
+            LURK_CUDA_TRY(cudaFuncSetAttribute(msm_pair_kernel<Fb, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_B * 4096));
+            attr_done.push_back(dev);
         }
     }
     if (ctx->profile) LURK_CUDA_TRY(cudaEventRecord(ctx->ev0, s));
-    if (fixed)
+    // ---- pair rounds (batched-affine additions) in front of the XYZZ accumulation, when the runs are long enough to pair
+    const size_t cap = n * (size_t)P.nwin;
+    int rounds = 0;
+    {
+        static const int forced = [] { const char *e = getenv("LURK_MSM_PAIR_ROUNDS"); return e ? atoi(e) : -1; }();   // tuning aid
+        const size_t avg = cap / TB;
+        if (forced >= 0) rounds = forced;
+        else if (n >= 8192) rounds = avg >= 12 ? 2 : (avg >= 5 ? 1 : 0);
+        if (rounds > 4) rounds = 4;
+    }
+    const uint32_t *acc_offs = offsets;
+    const Affine<Fb> *acc_pts = bases;
+    size_t cap_r = cap;
+    for (int r = 0; r < rounds; r++) {
+        cap_r = cap_r / 2 + TB + 1;                                        // sum of ceil(m_k / 2) <= cap / 2 + buckets
+        DevBuf &ob = S.pair_offs[r & 1], &pb = S.pair_pts[r & 1];
+        if (ob.bytes < ((size_t)TB + 1) * sizeof(uint32_t)) LURK_TRY(ob.alloc(((size_t)TB + 1) * sizeof(uint32_t)));
+        if (pb.bytes < cap_r * sizeof(Affine<Fb>)) LURK_TRY(pb.alloc(cap_r * sizeof(Affine<Fb>)));
+        uint32_t *o2 = ob.as<uint32_t>();
+        msm_halve_kernel<<<(TB + 256) / 256, 256, 0, s>>>(acc_offs, TB, counts);          // `counts` is free after the scatter
+        msm_scan_tile_sums_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_sums);
+        msm_scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_sums, ntiles, tile_offsets);
+        msm_scan_apply_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_offsets, ntiles, o2);
+        const size_t pthreads = (cap_r + PAIR_B - 1) / PAIR_B;
+        const unsigned pgrid = (unsigned)((pthreads + 127) / 128);
+        if (r == 0) msm_pair_kernel<Fb, true><<<pgrid, 128, PAIR_B * 4096, s>>>(acc_offs, o2, TB, sorted, acc_pts, pb.as<Affine<Fb>>());
+        else msm_pair_kernel<Fb, false><<<pgrid, 128, PAIR_B * 4096, s>>>(acc_offs, o2, TB, sorted, acc_pts, pb.as<Affine<Fb>>());
+        launches += 5;
+        acc_offs = o2;
+        acc_pts = pb.as<Affine<Fb>>();
+    }
+    const uint32_t t1 = rounds ? (uint32_t)((cap_r + P.seg - 1) / P.seg) : P.t1;
+    if (rounds)
+        msm_accumulate_kernel<Fb, 5, true><<<(t1 + 127) / 128, 128, pad, s>>>(acc_offs, TB, sorted, acc_pts, buckets, S.pkey[0].as<uint32_t>(),
+                                                                              S.ppt[0].as<Pt>(), P.seg, t1);
+    else if (fixed)
         msm_accumulate_kernel<Fb, 5><<<(P.t1 + 127) / 128, 128, pad, s>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
-                                                                       S.ppt[0].as<Pt>(), P.seg, P.t1);
+                                                                         S.ppt[0].as<Pt>(), P.seg, P.t1);
     else
         msm_accumulate_kernel<Fb, 4><<<(P.t1 + 127) / 128, 128, pad, s>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
-                                                                       S.ppt[0].as<Pt>(), P.seg, P.t1);
+                                                                         S.ppt[0].as<Pt>(), P.seg, P.t1);
     if (ctx->profile) LURK_CUDA_TRY(cudaEventRecord(ctx->ev1, s));
     launches += 6;
     // shrinking passes over the partial list: one throughput-shaped pass (8 entries per thread), then warp-cooperative
     // passes (32x per pass, 5 dependent additions each) until a single warp finishes
-    uint32_t count = P.t1;
+    uint32_t count = t1;
     int cur = 0;
     if (count > 32) {
         const uint32_t seg2 = 8, threads = (count + seg2 - 1) / seg2;
