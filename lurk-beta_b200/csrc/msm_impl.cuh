@@ -284,12 +284,15 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate_kernel(const uint32_
 // ---- pair rounds: batched-affine additions in front of the XYZZ accumulation ------------------------------------------------
 // A mixed XYZZ addition costs 10 field products; an AFFINE addition costs 3 (lambda = dy / dx; x3 = lambda^2 - x1 - x2;
 // y3 = lambda (x1 - x3) - y1) plus one inversion -- and inversions batch: Montgomery's trick turns the inversions of a whole CTA
-// (128 threads x PAIR_B additions) into ONE inversion (binary GCD, on the ALU pipe, by one thread) + 3 products per addition + a
-// dozen products per thread for the cross-thread prefix / suffix products.  ~7 products per addition instead of 10.
+// warp (32 threads x PAIR_B additions) into ONE inversion (binary GCD, on the ALU pipe, by one lane) + 3 products per addition + a
+// dozen products per thread for the cross-lane prefix / suffix products.  ~7 products per addition instead of 10.
 // Independent additions come from the sorted list itself: inside every bucket's run, entries 2j and 2j + 1 are added pairwise (an odd
 // tail is copied), which halves every run: out run k has ceil(m_k / 2) affine points.  One or two such rounds (half resp. three
 // quarters of all additions) run before the fixed-length-segment XYZZ accumulation takes the rest.
 static constexpr int PAIR_B = 16;        // output points per thread and batch
+// default number of pair rounds for long / short average runs: 0 = off (measured slower than the plain XYZZ accumulation on
+// B200 as implemented: the per-batch inversion stalls its CTA; profiles/r2_ncu_summary.md) -- LURK_MSM_PAIR_ROUNDS overrides
+static constexpr int MSM_PAIR_ROUNDS_LONG = 0, MSM_PAIR_ROUNDS_SHORT = 0;
 
 static __global__ void __launch_bounds__(256) msm_halve_kernel(const uint32_t *__restrict__ offs_in, uint32_t nbuckets, uint32_t *__restrict__ counts_out) {
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k <= nbuckets; k += gridDim.x * blockDim.x)
@@ -332,13 +335,12 @@ __device__ __forceinline__ Fb pair_denominator(const PairIn<Fb> &in) {
     return Fb::one();
 }
 
-// 1 / v for every thread of a 128-thread CTA with ONE field inversion (v != 0 everywhere)
+// 1 / v for every lane of a warp with ONE field inversion (v != 0 everywhere): inclusive prefix and suffix products by shuffles,
+// lane 31 inverts the total (binary GCD: shifts and adds on the ALU pipe, the multiplier stays free for the other warps of the SM)
 template <class Fb>
-__device__ __forceinline__ Fb block_batch_inverse(const Fb &v) {
-    __shared__ Fb warp_tot[4];
-    __shared__ Fb warp_inv[4];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    Fb pre = v, suf = v;                       // inclusive prefix / suffix products inside the warp
+__device__ __forceinline__ Fb warp_batch_inverse(const Fb &v) {
+    const int lane = threadIdx.x & 31;
+    Fb pre = v, suf = v;
 #pragma unroll 1
     for (int d = 1; d < 32; d <<= 1) {
         Fb a, b;
@@ -347,75 +349,56 @@ __device__ __forceinline__ Fb block_batch_inverse(const Fb &v) {
         if (lane >= d) pre = pre * a;
         if (lane + d < 32) suf = suf * b;
     }
-    if (lane == 31) warp_tot[w] = pre;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const Fb t0 = warp_tot[0], t1 = warp_tot[1], t2 = warp_tot[2], t3 = warp_tot[3];
-        const Fb t01 = t0 * t1, t23 = t2 * t3;
-        const Fb inv = (t01 * t23).inv_vartime();
-        const Fb i01 = inv * t23, i23 = inv * t01;        // 1 / (t0 t1), 1 / (t2 t3)
-        warp_inv[0] = i01 * t1; warp_inv[1] = i01 * t0; warp_inv[2] = i23 * t3; warp_inv[3] = i23 * t2;
-    }
-    __syncthreads();
-    Fb ep, es;                                  // exclusive prefix / suffix
+    Fb inv = Fb::zero();
+    if (lane == 31) inv = pre.inv_vartime();
+    Fb ep, es, r;                                  // exclusive prefix / suffix, inverse of the warp total
 #pragma unroll
-    for (int i = 0; i < 8; i++) { ep.v[i] = __shfl_up_sync(0xffffffffu, pre.v[i], 1); es.v[i] = __shfl_down_sync(0xffffffffu, suf.v[i], 1); }
-    Fb r = warp_inv[w];
+    for (int i = 0; i < 8; i++) {
+        ep.v[i] = __shfl_up_sync(0xffffffffu, pre.v[i], 1);
+        es.v[i] = __shfl_down_sync(0xffffffffu, suf.v[i], 1);
+        r.v[i] = __shfl_sync(0xffffffffu, inv.v[i], 31);
+    }
     if (lane > 0) r = r * ep;
     if (lane < 31) r = r * es;
-    __syncthreads();                            // the shared arrays are reused by the next batch
     return r;
 }
 
 // One pair round.  offs_in / offs_out: bucket offsets of the input / output lists (offs_out = scan of ceil(m / 2)).
-// Thread t produces output slots [t * PAIR_B, (t + 1) * PAIR_B).
+// Thread t produces output slots [t * PAIR_B, (t + 1) * PAIR_B); a warp shares one inversion per batch of 32 x PAIR_B additions.
 template <class Fb, bool FIRST>
 __global__ void __launch_bounds__(128) msm_pair_kernel(const uint32_t *__restrict__ offs_in, const uint32_t *__restrict__ offs_out, uint32_t nbuckets,
                                                        const uint32_t *__restrict__ sorted, const Affine<Fb> *__restrict__ pts_in,
                                                        Affine<Fb> *__restrict__ pts_out) {
-    extern __shared__ __align__(16) unsigned char pair_smem[];
-    uint4 *pp = reinterpret_cast<uint4 *>(pair_smem);            // prefix products [j][half][thread]
     const uint32_t total = offs_out[nbuckets];
-    const uint32_t tid = threadIdx.x;
-    const uint64_t start64 = ((uint64_t)blockIdx.x * blockDim.x + tid) * PAIR_B;
-    if ((uint64_t)blockIdx.x * blockDim.x * PAIR_B >= total) return;          // the whole CTA is past the end
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((gtid & ~31ull) * PAIR_B >= total) return;                              // the whole warp is past the end
+    const uint64_t start64 = gtid * PAIR_B;
     const bool active = start64 < total;
     const uint32_t start = active ? (uint32_t)start64 : 0, end = active ? (uint32_t)min((uint64_t)total, start64 + PAIR_B) : 0;
-    uint32_t k0 = 0;
+    uint32_t k = 0;
     if (active) {
         uint32_t lo = 0, hi = nbuckets;
         while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (offs_out[mid] <= start) lo = mid; else hi = mid; }
-        k0 = lo;
+        k = lo;
     }
-    auto put = [&](int j, const Fb &x) {
-        pp[(j * 2 + 0) * 128 + tid] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
-        pp[(j * 2 + 1) * 128 + tid] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
-    };
-    auto get = [&](int j) {
-        const uint4 a = pp[(j * 2 + 0) * 128 + tid], b = pp[(j * 2 + 1) * 128 + tid];
-        Fb x;
-        x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w; x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
-        return x;
-    };
-    // pass 1: running product of the denominators
+    Fb pref[PAIR_B];                                 // running products of the denominators (thread-private, L1-resident)
     Fb run = Fb::one();
-    uint32_t k = k0;
     for (uint32_t q = start; q < end; q++) {
         while (offs_out[k + 1] <= q) k++;
         const uint32_t in = offs_in[k] + 2 * (q - offs_out[k]);
         const PairIn<Fb> pi = pair_fetch<Fb, FIRST>(sorted, pts_in, in, offs_in[k + 1]);
         run = run * pair_denominator(pi);
-        put((int)(q - start), run);
+        pref[q - start] = run;
     }
-    Fb inv = block_batch_inverse(run);          // 1 / (product of this thread's denominators)
-    // pass 2, backwards: peel one denominator at a time
+    Fb inv = warp_batch_inverse(run);              // 1 / (product of this thread's denominators)
+    // backwards: peel one denominator at a time
     for (uint32_t q = end; q-- > start;) {
         while (offs_out[k] > q) k--;
         const uint32_t in = offs_in[k] + 2 * (q - offs_out[k]);
         const PairIn<Fb> pi = pair_fetch<Fb, FIRST>(sorted, pts_in, in, offs_in[k + 1]);
-        const int j = (int)(q - start);
+        const uint32_t j = q - start;
         const Fb den = pair_denominator(pi);
-        const Fb inv_d = j ? inv * get(j - 1) : inv;     // 1 / den
+        const Fb inv_d = j ? inv * pref[j - 1] : inv;     // 1 / den
         inv = inv * den;
         Affine<Fb> o = pi.p1;
         if (pi.kind == 3) { o.x = Fb::zero(); o.y = Fb::zero(); }
@@ -780,6 +763,20 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
     if ((uint64_t)n * (uint64_t)P.nwin >= (1ull << 32)) { set_error("%zu scalars exceed one launch (shard the commitment key)", n); return LURK_ERR_ARG; }
     const uint32_t TB = P.total_buckets;
     const uint32_t ntiles = (TB + SCAN_TILE - 1) / SCAN_TILE;
+    // pair rounds (batched-affine additions in front of the XYZZ accumulation): only when the runs are long enough to pair
+    const size_t cap = n * (size_t)P.nwin;
+    int rounds = 0;
+    {
+        static const int forced = [] { const char *e = getenv("LURK_MSM_PAIR_ROUNDS"); return e ? atoi(e) : -1; }();   // tuning aid
+        const size_t avg = cap / TB;
+        if (forced >= 0) rounds = forced;
+        else if (n >= 8192) rounds = avg >= 12 ? MSM_PAIR_ROUNDS_LONG : (avg >= 5 ? MSM_PAIR_ROUNDS_SHORT : 0);
+        if (rounds > 4) rounds = 4;
+    }
+    size_t cap_final = cap;
+    for (int r = 0; r < rounds; r++) cap_final = cap_final / 2 + TB + 1;       // sum of ceil(m_k / 2) <= cap / 2 + buckets
+    const uint32_t t1 = rounds ? (uint32_t)((cap_final + P.seg - 1) / P.seg) : P.t1;
+    const uint32_t t1_alloc = std::max(t1, P.t1);
     {
         // scratch grows monotonically; a context is normally run at one size (the circuit's witness length)
         auto ensure = [](DevBuf &b, size_t bytes) { return b.bytes >= bytes ? LURK_OK : b.alloc(bytes); };
@@ -788,9 +785,9 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
         LURK_TRY(ensure(S.tiles, ((size_t)ntiles + 1) * 2 * sizeof(uint32_t)));  // tile sums | tile offsets
         LURK_TRY(ensure(S.sorted, n * (size_t)P.nwin * sizeof(uint32_t)));
         LURK_TRY(ensure(S.buckets, (size_t)TB * sizeof(Pt)));
-        LURK_TRY(ensure(S.pkey[0], (size_t)P.t1 * sizeof(uint32_t)));
-        LURK_TRY(ensure(S.ppt[0], (size_t)P.t1 * sizeof(Pt)));
-        size_t t2 = ((size_t)P.t1 + 7) / 8;
+        LURK_TRY(ensure(S.pkey[0], (size_t)t1_alloc * sizeof(uint32_t)));
+        LURK_TRY(ensure(S.ppt[0], (size_t)t1_alloc * sizeof(Pt)));
+        size_t t2 = ((size_t)t1_alloc + 7) / 8;
         LURK_TRY(ensure(S.pkey[1], t2 * sizeof(uint32_t)));
         LURK_TRY(ensure(S.ppt[1], t2 * sizeof(Pt)));
         const size_t nchunks_all = (size_t)P.rwin * P.G;
@@ -833,22 +830,11 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
             LURK_CUDA_TRY(cudaFuncSetAttribute(msm_accumulate_kernel<Fb, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             LURK_CUDA_TRY(cudaFuncSetAttribute(msm_accumulate_kernel<Fb, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             LURK_CUDA_TRY(cudaFuncSetAttribute(msm_accumulate_kernel<Fb, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            LURK_CUDA_TRY(cudaFuncSetAttribute(msm_pair_kernel<Fb, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_B * 4096));
-            LURK_CUDA_TRY(cudaFuncSetAttribute(msm_pair_kernel<Fb, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_B * 4096));
             attr_done.push_back(dev);
         }
     }
     if (ctx->profile) LURK_CUDA_TRY(cudaEventRecord(ctx->ev0, s));
-    // ---- pair rounds (batched-affine additions) in front of the XYZZ accumulation, when the runs are long enough to pair
-    const size_t cap = n * (size_t)P.nwin;
-    int rounds = 0;
-    {
-        static const int forced = [] { const char *e = getenv("LURK_MSM_PAIR_ROUNDS"); return e ? atoi(e) : -1; }();   // tuning aid
-        const size_t avg = cap / TB;
-        if (forced >= 0) rounds = forced;
-        else if (n >= 8192) rounds = avg >= 12 ? 2 : (avg >= 5 ? 1 : 0);
-        if (rounds > 4) rounds = 4;
-    }
+    // ---- pair rounds
     const uint32_t *acc_offs = offsets;
     const Affine<Fb> *acc_pts = bases;
     size_t cap_r = cap;
@@ -864,13 +850,12 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
         msm_scan_apply_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_offsets, ntiles, o2);
         const size_t pthreads = (cap_r + PAIR_B - 1) / PAIR_B;
         const unsigned pgrid = (unsigned)((pthreads + 127) / 128);
-        if (r == 0) msm_pair_kernel<Fb, true><<<pgrid, 128, PAIR_B * 4096, s>>>(acc_offs, o2, TB, sorted, acc_pts, pb.as<Affine<Fb>>());
-        else msm_pair_kernel<Fb, false><<<pgrid, 128, PAIR_B * 4096, s>>>(acc_offs, o2, TB, sorted, acc_pts, pb.as<Affine<Fb>>());
+        if (r == 0) msm_pair_kernel<Fb, true><<<pgrid, 128, 0, s>>>(acc_offs, o2, TB, sorted, acc_pts, pb.as<Affine<Fb>>());
+        else msm_pair_kernel<Fb, false><<<pgrid, 128, 0, s>>>(acc_offs, o2, TB, sorted, acc_pts, pb.as<Affine<Fb>>());
         launches += 5;
         acc_offs = o2;
         acc_pts = pb.as<Affine<Fb>>();
     }
-    const uint32_t t1 = rounds ? (uint32_t)((cap_r + P.seg - 1) / P.seg) : P.t1;
     if (rounds)
         msm_accumulate_kernel<Fb, 5, true><<<(t1 + 127) / 128, 128, pad, s>>>(acc_offs, TB, sorted, acc_pts, buckets, S.pkey[0].as<uint32_t>(),
                                                                               S.ppt[0].as<Pt>(), P.seg, t1);
