@@ -26,7 +26,6 @@ static constexpr int FOLD_MAX_WORLD = 16;
 static constexpr int FOLD_MAX_DEPTH = 4;
 static constexpr int FOLD_MAX_SPANS = 4;
 static constexpr int FOLD_RO_RATE = 24;            // Arecibo's RO: neptune sponge over PoseidonConstants<_, U24>
-static constexpr int FOLD_W_SMEM_KB = 0;            // occupancy cap of the prefetched commit(W)'s accumulate kernel (see lurk_msm_ctx::acc_smem_pad)
 static constexpr int FOLD_T_WINDOW = 16;           // widest window of the chain-critical commit(T) (measured: profiles/r2_ncu_summary.md)
 
 // ----------------------------------------------------------------------------- fold kernels (witness field)

@@ -78,8 +78,6 @@ struct FoldCtx final : FoldCtxBase {
     bool a_recorded[FOLD_MAX_DEPTH] = {false, false, false, false};
     bool b_pending[FOLD_MAX_DEPTH + 1] = {false, false, false, false, false};
     bool running_set = false;
-    cudaEvent_t ev_tail = nullptr;    // bucket reduction of the chain's commit(T) enqueued (gates the prefetched commit(W))
-    bool tail_recorded = false;
     bool mv1_valid = false;           // mv1 = (A z1, B z1, C z1) is kept current by the fold itself
     unsigned launches_a = 0, launches_b = 0;
     int device = 0;
@@ -117,7 +115,6 @@ struct FoldCtx final : FoldCtxBase {
         if (ckT) lurk_msm_ctx_destroy(ckT);
         if (ckChk) lurk_msm_ctx_destroy(ckChk);
         if (ckChkW) lurk_msm_ctx_destroy(ckChkW);
-        if (ev_tail) cudaEventDestroy(ev_tail);
         for (auto &sb : batches)
             for (int b = 0; b < FOLD_MAX_DEPTH; b++)
                 if (sb->h_pre[b]) cudaFreeHost(sb->h_pre[b]);
@@ -211,28 +208,13 @@ struct FoldCtx final : FoldCtxBase {
         }
         LURK_TRY(lurk_msm_ctx_clone(ck_t, &ckChk));
         LURK_TRY(lurk_msm_ctx_clone(ck_w, &ckChkW));     // check_running must not touch a prefetched commit(W2)
-        {
-            static const int w_pad_kb = [] { const char *e = getenv("LURK_FOLD_W_SMEM_KB"); return e ? atoi(e) : FOLD_W_SMEM_KB; }();   // tuning aid
-            for (int b = 0; b < D; b++) ckW[b]->acc_smem_pad = (unsigned)w_pad_kb * 1024u;
-        }
         for (int b = 0; b < D; b++) lurk_msm_ctx_set_profiling(ckW[b], 1);
         lurk_msm_ctx_set_profiling(ckT, 1);
 
         // streams: the chain gets the high priority; optional SM partition
         int lo = 0, hi = 0;
         LURK_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        static const bool stage_a_partition = getenv("LURK_FOLD_PARTITION_STAGE_A") != nullptr;   // experiment: see profiles/r2_ncu_summary.md
-        if (c.latency_sms > 0 && stage_a_partition) {
-            // the other split: `latency_sms` SMs for ALL of stage A (slot witnesses, commit(W), A z2..), the rest for the chain
-            cudaStream_t small[4] = {nullptr, nullptr, nullptr, nullptr}, big_lo[1] = {nullptr};
-            if (green_streams(c.latency_sms, small, 4, &sB, big_lo, 1) != LURK_OK) {
-                set_error("SM partitioning (green contexts) is not available on this driver");
-                return LURK_ERR_CUDA;
-            }
-            sK[0] = small[0]; sK[1] = small[1]; sK[2] = small[2]; sA = small[3];
-            sC = big_lo[0];
-            sT = sB;
-        } else if (c.latency_sms > 0) {
+        if (c.latency_sms > 0) {
             cudaStream_t tiny[2] = {nullptr, nullptr}, big_lo[4] = {nullptr, nullptr, nullptr, nullptr};
             if (green_streams(c.latency_sms, tiny, 2, &sB, big_lo, 4) != LURK_OK) {
                 set_error("SM partitioning (green contexts) is not available on this driver");
@@ -263,7 +245,6 @@ struct FoldCtx final : FoldCtxBase {
             for (int k = 0; k < 3; k++) LURK_CUDA_TRY(mkev(&ev_slot[b][k]));
         }
         for (int b = 0; b <= D; b++) { LURK_CUDA_TRY(mkev(&ev_chal[b])); LURK_CUDA_TRY(mkev(&ev_done[b])); }
-        LURK_CUDA_TRY(mkev(&ev_tail));
 
         // vectors
         LURK_TRY(z1.alloc(nz * sizeof(Fs)));
@@ -628,11 +609,7 @@ struct FoldCtx final : FoldCtxBase {
         }
         for (int s = 0; s < 3; s++) LURK_CUDA_TRY(cudaEventRecord(ev_slot[b][s], sK[s]));
         for (int s = 1; s < 3; s++) LURK_CUDA_TRY(cudaStreamWaitEvent(sK[0], ev_slot[b][s], 0));
-        // comm_W2 (this rank's share): result stays on the device for the challenge kernel.  Optionally gated behind the bucket
-        // reduction of the fold in flight, so that the throughput-shaped accumulation of the NEXT step's witness fills the GPU
-        // while the chain sits in its single-warp kernels instead of slowing the chain's wide tail kernels (LURK_FOLD_GATE_W)
-        static const bool gate_w = getenv("LURK_FOLD_GATE_W") != nullptr;
-        if (gate_w && tail_recorded) LURK_CUDA_TRY(cudaStreamWaitEvent(sK[0], ev_tail, 0));
+        // comm_W2 (this rank's share): result stays on the device for the challenge kernel
         LURK_TRY(msm_launch<C>(ckW[b], W2, cfg.n_w, LURK_FMT_MONTGOMERY, sK[0], false));
         k += ckW[b]->last_launches;
         LURK_CUDA_TRY(cudaEventRecord(ev_cw[b], partitioned ? sT : sK[0]));   // where msm_horner_kernel ran
@@ -735,8 +712,6 @@ struct FoldCtx final : FoldCtxBase {
         }
         LURK_TRY(msm_launch<C>(ckT, T.p, rows, LURK_FMT_MONTGOMERY, sB, false));
         k += rows ? ckT->last_launches : 0;
-        LURK_CUDA_TRY(cudaEventRecord(ev_tail, sB));
-        tail_recorded = true;
         // the finished partial commitments are on sT (the tiny partition's stream, or sB itself without a partition)
         if (sT != sB && !rows) {           // an empty T is produced by a memset on sB
             LURK_CUDA_TRY(cudaEventRecord(ev_chal[b], sB));

@@ -703,11 +703,6 @@ struct lurk_msm_ctx {
     // that they do not share an SM's multiplier pipe with thousands of bucket-accumulation warps.  Without read-back the
     // result is then ready on `tiny_stream`, not on the caller's stream.
     cudaStream_t tiny_stream = nullptr;
-    // Occupancy cap of the bucket-accumulation kernel for commitments that run UNDER a latency-critical chain (the prefetched
-    // commit(W) of the fold context): the kernel is launched with this much unused dynamic shared memory, so that fewer of its
-    // CTAs are resident per SM and the chain's short kernels always find free registers / CTA slots instead of waiting for
-    // ~0.2 ms long accumulate CTAs to retire.  0 = full occupancy.
-    unsigned acc_smem_pad = 0;
     // Optional constant part of the scalar vector (set by the fold context; device-resident results only): when most of a
     // vector repeats a fixed vector d from call to call -- the dummy slot witnesses of a Lurk step (src/lem/multiframe.rs:553-577:
     // unused slots share one cached witness) -- the context commits to s - d, whose entries vanish wherever s repeats d and
@@ -818,21 +813,6 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
     msm_scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_sums, ntiles, tile_offsets);
     msm_scan_apply_kernel<<<ntiles, 1024, 0, s>>>(counts, TB, tile_offsets, ntiles, offsets);
     msm_scatter_kernel<Fs><<<gs, 256, 0, s>>>((const Fs *)d_scalars, sub, n, fmt, P.c, P.nwin, key_stride, base_stride, offsets, cursor, sorted);
-    const unsigned pad = ctx->acc_smem_pad;
-    {
-        // one-off per device: opt-ins for dynamic shared memory (the pair kernels' prefix products; the optional occupancy pad)
-        static std::mutex attr_mu;
-        static std::vector<int> attr_done;
-        int dev = 0;
-        LURK_CUDA_TRY(cudaGetDevice(&dev));
-        std::lock_guard<std::mutex> g(attr_mu);
-        if (std::find(attr_done.begin(), attr_done.end(), dev) == attr_done.end()) {
-            LURK_CUDA_TRY(cudaFuncSetAttribute(msm_accumulate_kernel<Fb, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            LURK_CUDA_TRY(cudaFuncSetAttribute(msm_accumulate_kernel<Fb, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            LURK_CUDA_TRY(cudaFuncSetAttribute(msm_accumulate_kernel<Fb, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done.push_back(dev);
-        }
-    }
     if (ctx->profile) LURK_CUDA_TRY(cudaEventRecord(ctx->ev0, s));
     // ---- pair rounds
     const uint32_t *acc_offs = offsets;
@@ -857,13 +837,13 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
         acc_pts = pb.as<Affine<Fb>>();
     }
     if (rounds)
-        msm_accumulate_kernel<Fb, 5, true><<<(t1 + 127) / 128, 128, pad, s>>>(acc_offs, TB, sorted, acc_pts, buckets, S.pkey[0].as<uint32_t>(),
+        msm_accumulate_kernel<Fb, 5, true><<<(t1 + 127) / 128, 128, 0, s>>>(acc_offs, TB, sorted, acc_pts, buckets, S.pkey[0].as<uint32_t>(),
                                                                               S.ppt[0].as<Pt>(), P.seg, t1);
     else if (fixed)
-        msm_accumulate_kernel<Fb, 5><<<(P.t1 + 127) / 128, 128, pad, s>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
+        msm_accumulate_kernel<Fb, 5><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
                                                                          S.ppt[0].as<Pt>(), P.seg, P.t1);
     else
-        msm_accumulate_kernel<Fb, 4><<<(P.t1 + 127) / 128, 128, pad, s>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
+        msm_accumulate_kernel<Fb, 4><<<(P.t1 + 127) / 128, 128, 0, s>>>(offsets, TB, sorted, bases, buckets, S.pkey[0].as<uint32_t>(),
                                                                          S.ppt[0].as<Pt>(), P.seg, P.t1);
     if (ctx->profile) LURK_CUDA_TRY(cudaEventRecord(ctx->ev1, s));
     launches += 6;
