@@ -47,7 +47,7 @@ struct FoldCtx final : FoldCtxBase {
     size_t nz = 0;                          // |z| = n_w + 1 + n_x
     int D = 2;
     lurk_msm_ctx *ckW[FOLD_MAX_DEPTH] = {nullptr, nullptr, nullptr, nullptr};
-    lurk_msm_ctx *ckT = nullptr, *ckChk = nullptr, *ckChkW = nullptr;
+    lurk_msm_ctx *ckT = nullptr, *ckChk = nullptr, *ckChkW = nullptr, *ckWbase = nullptr;
     DevBuf z1, e1, T, mv1[3], z2[FOLD_MAX_DEPTH], mv2[FOLD_MAX_DEPTH][3];
     DevBuf csr_rp[3], csr_col[3], csr_val[3];
     CsrDev csr[3];
@@ -115,6 +115,7 @@ struct FoldCtx final : FoldCtxBase {
         if (ckT) lurk_msm_ctx_destroy(ckT);
         if (ckChk) lurk_msm_ctx_destroy(ckChk);
         if (ckChkW) lurk_msm_ctx_destroy(ckChkW);
+        if (ckWbase) lurk_msm_ctx_destroy(ckWbase);
         for (auto &sb : batches)
             for (int b = 0; b < FOLD_MAX_DEPTH; b++)
                 if (sb->h_pre[b]) cudaFreeHost(sb->h_pre[b]);
@@ -190,7 +191,21 @@ struct FoldCtx final : FoldCtxBase {
         // fixed-base tables: the device-side finish of a commitment needs one bucket set (msm_horner_kernel)
         LURK_TRY(lurk_msm_ctx_precompute(ck_w));
         if (ck_t != ck_w) LURK_TRY(lurk_msm_ctx_precompute(ck_t));
-        for (int b = 0; b < D; b++) LURK_TRY(lurk_msm_ctx_clone(ck_w, &ckW[b]));
+        {
+            // commit(W2 - D): after the dummy-witness offset only ~a third of the scalars are non-zero, so the 2^(c-1)-bucket
+            // reduction weighs more against the per-window additions than for a dense vector: own narrower table when it pays
+            static const int w_window_env = [] { const char *e = getenv("LURK_FOLD_W_WINDOW"); return e ? atoi(e) : 0; }();   // tuning aid
+            const int want = std::min(ck_w->fixed_c, w_window_env ? w_window_env : FOLD_W_WINDOW);
+            LURK_TRY(lurk_msm_ctx_clone(ck_w, &ckWbase));
+            if (want != ck_w->fixed_c && c.n_w) {
+                ckWbase->n = c.n_w;
+                ckWbase->d_table = nullptr;
+                ckWbase->owns_table = false;
+                ckWbase->fixed_c = 0;
+                LURK_TRY(msm_precompute<C>(ckWbase, want));
+            }
+            for (int b = 0; b < D; b++) LURK_TRY(lurk_msm_ctx_clone(ckWbase, &ckW[b]));
+        }
         LURK_TRY(lurk_msm_ctx_clone(ck_t, &ckT));
         {
             // commit(T) sits on the sequential chain: a narrower window than the throughput optimum shortens the bucket
