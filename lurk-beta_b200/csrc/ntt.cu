@@ -6,8 +6,8 @@
 //   * twiddles omega^j, j < n/2, are generated once per (field, log_n, direction) and cached on the device;
 //   * the first min(log_n, 10) butterfly stages run inside shared memory on 1024-element tiles after a
 //     bit-reversal gather (one global read + one global write for 10 stages);
-//   * the remaining stages are strided global passes, three stages (radix-8) per pass where possible; the last pass writes
-//     into the caller's buffer (no trailing copy).  2^24: 1 + 5 passes (round 1: 1 + 7 passes + a copy).
+//   * the remaining stages are strided global passes, two stages (radix-4) per pass where possible; the last pass writes
+//     into the caller's buffer (no trailing copy).
 // For 256-bit fields the butterflies' multiplier work (12 x 2^24 products = 2.9 ms on the IMAD pipe at 2^24) exceeds the HBM
 // time of the passes, so the transform is multiply bound like the rest of the path.  A variant that ran
 // stages 11..20 on shared-memory column tiles (4 global passes instead of 9) was measured slower (4.7 ms) in round 1 and dropped.
@@ -91,43 +91,6 @@ __global__ void __launch_bounds__(256) ntt_stage2_kernel(const F *src, F *dst, c
     }
 }
 
-// three global stages s, s+1, s+2 fused (radix-8 butterfly): 8 loads + 8 stores and 7 twiddle loads for three stages --
-// one global pass less per three stages than the radix-4 form (the transform is multiplier bound, but every pass also costs
-// 64 B of HBM traffic per element and a grid-wide dependency)
-template <class F>
-__global__ void __launch_bounds__(256) ntt_stage3_kernel(const F *src, F *dst, const F *__restrict__ tw, int log_n, int s) {
-    const size_t n8 = (size_t)1 << (log_n - 3);
-    const size_t half = (size_t)1 << (s - 1);
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n8; k += (size_t)gridDim.x * blockDim.x) {
-        const size_t j = k & (half - 1);
-        const size_t i0 = ((k >> (s - 1)) << (s + 2)) + j;
-        F x[8];
-#pragma unroll
-        for (int m = 0; m < 8; m++) x[m] = load_fe<F>(src + i0 + m * half);
-        {   // stage s: pairs (m, m + 1), one twiddle
-            const F w = load_fe<F>(tw + (j << (log_n - s)));
-#pragma unroll
-            for (int m = 0; m < 8; m += 2) { const F t = w * x[m + 1]; x[m + 1] = x[m] - t; x[m] = x[m] + t; }
-        }
-        {   // stage s + 1: pairs (m, m + 2), twiddle of position j + (m & 1) half
-            const F wa = load_fe<F>(tw + (j << (log_n - s - 1))), wb = load_fe<F>(tw + ((j + half) << (log_n - s - 1)));
-#pragma unroll
-            for (int m = 0; m < 8; m += 4) {
-                F t = wa * x[m + 2]; x[m + 2] = x[m] - t; x[m] = x[m] + t;
-                t = wb * x[m + 3]; x[m + 3] = x[m + 1] - t; x[m + 1] = x[m + 1] + t;
-            }
-        }
-        // stage s + 2: pairs (m, m + 4), twiddle of position j + m half
-#pragma unroll
-        for (int m = 0; m < 4; m++) {
-            const F w = load_fe<F>(tw + ((j + m * half) << (log_n - s - 2)));
-            const F t = w * x[m + 4]; x[m + 4] = x[m] - t; x[m] = x[m] + t;
-        }
-#pragma unroll
-        for (int m = 0; m < 8; m++) store_fe(dst + i0 + m * half, x[m]);
-    }
-}
-
 template <class F>
 __global__ void __launch_bounds__(256) ntt_scale_kernel(const F *src, F *dst, size_t n, F k) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -180,17 +143,16 @@ static int ntt_run(void *d_data, int log_n, int inverse, cudaStream_t s) {
     const size_t smem = ((size_t)1 << tile_log) * sizeof(F);
     ntt_tile_kernel<F><<<(unsigned)(n >> tile_log), 512, smem, s>>>(a, tmp, tw, log_n, tile_log);
     const int grid = sm_count() * 8;
-    // remaining stages on the ping-pong buffer, three per pass (then two / one); the LAST pass of the whole transform writes
-    // back into the caller's buffer, so there is no trailing copy
+    // remaining stages on the ping-pong buffer, two per pass (radix-4; a radix-8 pass -- three stages, 120 registers -- was measured
+    // slower: 4.75 ms instead of 4.14 ms at 2^24); the LAST pass of the whole transform writes back into the caller's buffer, so
+    // there is no trailing copy
     int st = tile_log + 1;
     const int remaining = log_n - tile_log;
-    int passes = (remaining + 2) / 3 + (inverse ? 1 : 0);
+    int passes = (remaining + 1) / 2 + (inverse ? 1 : 0);
     auto dst_of = [&](void) { return --passes == 0 ? a : tmp; };
     while (st <= log_n) {
-        const int left = log_n - st + 1;
         F *dst = dst_of();
-        if (left >= 3) { ntt_stage3_kernel<F><<<grid, 256, 0, s>>>(tmp, dst, tw, log_n, st); st += 3; }
-        else if (left == 2) { ntt_stage2_kernel<F><<<grid, 256, 0, s>>>(tmp, dst, tw, log_n, st); st += 2; }
+        if (st + 1 <= log_n) { ntt_stage2_kernel<F><<<grid, 256, 0, s>>>(tmp, dst, tw, log_n, st); st += 2; }
         else { ntt_stage_kernel<F><<<grid, 256, 0, s>>>(tmp, dst, tw, log_n, st); st += 1; }
     }
     cudaError_t e = cudaGetLastError();
