@@ -339,7 +339,7 @@ class Instance:
 class FoldStepGPU:
     """one rank's share of the fold step of a workload, driven through the C-ABI fold context"""
 
-    def __init__(self, rank, world, scaling="weak", latency_sms=0, seed=0x6c75726b, workload="fib", rc=None):
+    def __init__(self, rank, world, scaling="weak", latency_sms=0, seed=0x6c75726b, workload="fib", rc=None, key="synthetic"):
         import torch
         import lurk_beta_b200 as L
         self.torch, self.L = torch, L
@@ -355,7 +355,19 @@ class FoldStepGPU:
         nW, nT = self.frames * per, self.frames * rows_pf
         # ---- commitment key: this rank's slices of the global key [i+1]G in the reference's layout (W index = frame * per + j,
         # T / E index = frame * rows_per_frame + j).  One resident power-of-two key serves both when nothing is sharded.
-        if world == 1:
+        self.key, self.ck_generate_ms = key, None
+        if key == "from_label":
+            # the reference's own key distribution (N3): DlogGroup::from_label(b"ck", n) generated on the GPU into device memory
+            t0 = time.perf_counter()
+            if world == 1:
+                n_key = L.ck_size(nT, nW, 1 << 14)
+                self.ck_w = self.ck_t = L.CommitmentKey.setup(CURVE, b"ck", n_key)
+            else:
+                self.ck_w = L.CommitmentKey.setup(CURVE, b"ck", nW, first=f0 * per)
+                self.ck_t = L.CommitmentKey.setup(CURVE, b"ck", nT, first=f0 * rows_pf)
+            torch.cuda.synchronize()
+            self.ck_generate_ms = (time.perf_counter() - t0) * 1e3
+        elif world == 1:
             n_key = 1 << max(14, (max(nW, nT) - 1).bit_length())
             self.ck_w = self.ck_t = L.CommitmentKey(CURVE, L.synthetic_bases(CURVE, n_key, fmt=M), fmt=M)
         else:
@@ -456,7 +468,21 @@ def verify_full_size(wl, rank):
         t.cuda.synchronize()
         both = both.cpu().numpy()
         W2c, Tc = both[:wl.nW * 32], both[wl.nW * 32:]
-        bases = oracle.gen_bases(CURVE, max(wl.nW, wl.nT))
+        if wl.key == "from_label":
+            # the checker gets the key as data (a copy generated through the host-buffer entry point); 8 of its points are compared
+            # with the Python restatement of from_label
+            from oracle import h2c
+            import hashlib
+            nk = max(wl.nW, wl.nT)
+            bases = L.from_label(CURVE, b"ck", nk)
+            stream_ = hashlib.shake_256(b"ck").digest(32 * nk)
+            for i in (0, 1, 65535, 65536, nk // 2, nk - 2, nk - 1, 12345):
+                x = int.from_bytes(bases[64 * i:64 * i + 32].tobytes(), "little")
+                y = int.from_bytes(bases[64 * i + 32:64 * i + 64].tobytes(), "little")
+                assert (x, y) == h2c.hash_to_curve(CURVE, "from_uniform_bytes", stream_[32 * i:32 * i + 32]), i
+            out["key_points_checked_against_oracle"] = 8
+        else:
+            bases = oracle.gen_bases(CURVE, max(wl.nW, wl.nT))
         want_w = oracle.msm(CURVE, bases, W2c, nthreads=th)
         want_t = oracle.msm(CURVE, bases, Tc, nthreads=th)
         r, h = spec.ro_squeeze(1, spec.nifs_absorb_list(PP_DIGEST, nifs.point_of(want_w), wl.X2, nifs.point_of(want_t)))
@@ -512,7 +538,7 @@ def run_gpu(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    wl = FoldStepGPU(rank, world, scaling=args.scaling, latency_sms=args.latency_sms, workload=args.workload, rc=args.rc)
+    wl = FoldStepGPU(rank, world, scaling=args.scaling, latency_sms=args.latency_sms, workload=args.workload, rc=args.rc, key=args.key)
     wl.ctx.connect()          # exchange-buffer handles through the process group (setup only; the steps never call NCCL)
 
     def barrier():
@@ -597,6 +623,9 @@ def run_gpu(args):
                                  "alone right after the timed region"},
             "clocks": clocks,
         }
+        if args.key != "synthetic":
+            out["config"]["key"] = "DlogGroup::from_label(b'ck') (hash-to-curve, generated on the GPU)"
+            out["setup"] = {"ck_generate_ms": round(wl.ck_generate_ms, 1), "note": "outside the timed region (the metric excludes public-parameter setup)"}
         if args.latency_sms:
             out["config"]["sm_partition"] = f"{args.latency_sms} SMs reserved for the latency-shaped kernels (green contexts)"
         if world == 1 and not args.no_cpu_baseline and args.workload == "fib":
@@ -720,6 +749,8 @@ def main():
     ap.add_argument("--live-slots", type=float, default=LIVE_SLOT_FRACTION,
                     help="fraction of a frame's slots with a non-dummy preimage (dummy slots share one witness, multiframe.rs:553-577)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--key", default="synthetic", choices=["synthetic", "from_label"],
+                    help="commitment key: [i+1]G (default; the CPU arm uses the same) or the reference's hash-to-curve key generated on the GPU (N3)")
     args = ap.parse_args()
     LIVE_SLOT_FRACTION = args.live_slots
     if args.impl == "reference":

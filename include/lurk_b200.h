@@ -177,6 +177,73 @@ int lurk_synthetic_bases(int curve_id, uint64_t start, size_t n, int fmt, uint8_
 int lurk_point_sum(int curve_id, const uint8_t *points_xyz, size_t count, int fmt, uint8_t out_xyz[96]);
 
 /* ---------------------------------------------------------------------------------------------------
+ * N3  Commitment-key generation.  Replaces what `public_params` (src/proof/nova.rs:196-216, supernova.rs:117-137; cached on
+ *     disk by src/public_parameters/mod.rs:20-71 because it takes minutes on the CPU) makes Arecibo do for the Pedersen key:
+ *     R1CSShape::commitment_key -> CommitmentKey::setup(b"ck", n), n = next_power_of_two(max(#cons, #vars, ck_floor)) ->
+ *     DlogGroup::from_label(label, n):  uniform_i = next 32 bytes of SHAKE256(label);
+ *     G_i = Curve::hash_to_curve("from_uniform_bytes")(uniform_i), affine.
+ *     hash_to_curve = halo2curves 0.6 (BN254 G1 / Grumpkin: BLAKE2b expand_message_xmd + Shallue-van de Woestijne, RFC 9380)
+ *     or pasta_curves 0.5 (Pallas / Vesta: same hash_to_field + simplified SWU on the 3-isogenous curve + isogeny).
+ *     The XOF is sequential and stays on a host thread, pipelined against the kernel that maps the points.
+ * ------------------------------------------------------------------------------------------------- */
+/* next_power_of_two(max(num_cons, num_vars, ck_floor)): the key length public_params asks for.  Host only. */
+size_t lurk_ck_size(size_t num_cons, size_t num_vars, size_t ck_floor);
+/* from_label: n affine points x | y (64 bytes each, identity = (0, 0)) in `fmt`. */
+int lurk_ck_generate(int curve_id, const uint8_t *label, size_t label_len, size_t n, int fmt, uint8_t *bases_out);
+/* same, written to device memory in Montgomery form -- exactly what lurk_msm_ctx_create_dev borrows: the key never crosses
+ * PCIe.  Returns when the key is complete (the host thread feeds the XOF stream while the GPU works). */
+int lurk_ck_generate_dev(int curve_id, const uint8_t *label, size_t label_len, size_t n, void *d_bases_mont, void *stream);
+/* points first .. first + n - 1 of the same key: a rank's contiguous slice of a key sharded over GPUs */
+int lurk_ck_generate_range_dev(int curve_id, const uint8_t *label, size_t label_len, size_t first, size_t n, void *d_bases_mont,
+                               void *stream);
+/* Curve::hash_to_curve(domain_prefix)(message) for n messages of msg_len bytes each (msg_len <= 64 and
+ * msg_len + strlen(domain_prefix) <= ~80: everything must fit the single-block layout, else LURK_ERR_ARG). */
+int lurk_hash_to_curve_batch(int curve_id, const char *domain_prefix, const uint8_t *messages, size_t msg_len, size_t n, int fmt,
+                             uint8_t *points_out);
+int lurk_hash_to_curve_batch_dev(int curve_id, const char *domain_prefix, const void *d_messages, size_t msg_len, size_t n,
+                                 void *d_points, int fmt, void *stream);
+/* SHAKE256(in) -> out_len bytes (FIPS 202).  Host only (works without a GPU); the XOF behind from_label. */
+int lurk_shake256(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len);
+
+/* ---------------------------------------------------------------------------------------------------
+ * N4  The data-parallel loops of `compress` (src/proof/nova.rs:341-356, supernova.rs:293-317 -> Arecibo CompressedSNARK::prove ->
+ *     spartan::snark::RelaxedR1CSSNARK::prove): sum-check prover rounds over device-resident multilinear polynomials
+ *     (SumcheckProof::prove_quad / prove_cubic_with_additive_term: compute_eval_points_* + bind_poly_var_top) and the folding rounds
+ *     of the inner-product argument (provider::ipa_pc::InnerProductArgument::prove), plus EqPolynomial::evals and the inner
+ *     product behind MultilinearPolynomial::evaluate.  The Fiat-Shamir transcript (Keccak256Transcript) stays on the caller's side:
+ *     every round passes its message to `challenge` and receives the verifier's challenge.  Polynomials: 2^num_rounds elements,
+ *     Montgomery form, index bit (num_rounds - 1) = the first variable (bound first), as in Arecibo's MultilinearPolynomial.
+ *     Not here: the transcript, proof (de)serialisation, HyperKZG (pairing side) and the verifier -- CPU / third-party protocol code.
+ * ------------------------------------------------------------------------------------------------- */
+/* message: the round's prover message in `fmt` -- sum-check: s(0) | s(1) | s(2) [| s(3)] (32 bytes each; Arecibo absorbs the
+ * compressed form, i.e. the coefficients without the linear one: the caller converts);  IPA: L | R as 96-byte points.
+ * Writes the challenge (32 bytes, `fmt`) and returns 0, or non-zero to abort the proof. */
+typedef int (*lurk_challenge_fn)(void *user, int round, const uint8_t *message, size_t message_len, uint8_t challenge_out[32]);
+#define LURK_SUMCHECK_QUAD 0  /* claim = sum_i A[i] B[i]                 d_polys = {A, B}          degree 2 */
+#define LURK_SUMCHECK_CUBIC 1 /* claim = sum_i A[i] (B[i] C[i] - D[i])   d_polys = {A, B, C, D}    degree 3 */
+/* Runs all num_rounds rounds.  The polynomials are consumed (bound in place; element 0 of each ends as its final evaluation).
+ * round_evals: num_rounds x (degree + 1) x 32 bytes; challenges: num_rounds x 32; final_evals: 2 or 4 x 32 (any may be NULL). */
+int lurk_sumcheck_prove_dev(int field_id, int kind, void *const *d_polys, int num_rounds, const uint8_t claim[32],
+                            lurk_challenge_fn challenge, void *user, uint8_t *round_evals, uint8_t *challenges, uint8_t *final_evals,
+                            int fmt, void *stream);
+/* EqPolynomial::new(tau).evals(): d_out[i] = prod_j (bit_j(i) ? tau[j] : 1 - tau[j]), tau[0] <-> the top index bit; 2^num_vars
+ * elements in `fmt` (tau: host, num_vars x 32 bytes, same fmt). */
+int lurk_eq_evals_dev(int field_id, const uint8_t *tau, int num_vars, void *d_out, int fmt, void *stream);
+/* <a, b> over n Montgomery elements (MultilinearPolynomial::evaluate = <Z, eq(r)>; the c_L / c_R of an IPA round).  Synchronous. */
+int lurk_inner_product_dev(int field_id, const void *d_a, const void *d_b, size_t n, uint8_t out[32], int fmt, void *stream);
+/* one IPA folding step, in place on the first n / 2 slots: a[i] <- x a[i] + y a[i + n/2];  G[i] <- x G[i] + y G[i + n/2]
+ * (CommitmentKey::fold; bases affine Montgomery; x, y host scalars in `fmt`). */
+int lurk_ipa_fold_scalars_dev(int field_id, void *d_a, size_t n, const uint8_t x[32], const uint8_t y[32], int fmt, void *stream);
+int lurk_ipa_fold_bases_dev(int curve_id, void *d_bases_mont, size_t n, const uint8_t x[32], const uint8_t y[32], int fmt, void *stream);
+/* All log_n rounds of InnerProductArgument::prove on device-resident a, b (scalars, Montgomery) and key G (2^log_n affine points,
+ * Montgomery), all three consumed: per round c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo>, L = commit(a_lo; G_hi) + c_L ck_c,
+ * R = commit(a_hi; G_lo) + c_R ck_c, r = challenge(L | R), a' = a_lo r + a_hi / r, b' = b_lo / r + b_hi r, G' = G_lo / r + G_hi r.
+ * ck_c: the (already scaled) base for the inner-product value, 64 bytes affine in `fmt`.  L_out / R_out: log_n x 96 bytes. */
+int lurk_ipa_prove_dev(int curve_id, void *d_bases_mont, const uint8_t ck_c[64], void *d_a, void *d_b, int log_n,
+                       lurk_challenge_fn challenge, void *user, uint8_t *L_out, uint8_t *R_out, uint8_t a_final[32], uint8_t b_final[32],
+                       int fmt, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * S5  Fold helpers on device-resident vectors (Arecibo NIFS::prove / R1CSShape::commit_T /
  *     RelaxedR1CSWitness::fold).  All vectors Montgomery form on the device.
  * ------------------------------------------------------------------------------------------------- */

@@ -47,6 +47,9 @@ FOLD_INPUTS_RESIDENT = 1
 FOLD_RO_CONST, FOLD_RO_W_X, FOLD_RO_W_Y, FOLD_RO_W_INF, FOLD_RO_T_X, FOLD_RO_T_Y, FOLD_RO_T_INF = range(7)
 
 _vp, _sz, _i = C.c_void_p, C.c_size_t, C.c_int
+# lurk_challenge_fn: int (*)(void *user, int round, const uint8_t *message, size_t message_len, uint8_t challenge_out[32])
+CHALLENGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_uint8))
+SUMCHECK_QUAD, SUMCHECK_CUBIC = 0, 1
 # every symbol declared in include/lurk_b200.h: name -> (restype, argtypes)
 PROTOTYPES = {
     "lurk_last_error": (C.c_char_p, []),
@@ -81,6 +84,19 @@ PROTOTYPES = {
     "lurk_msm_ctx_last_profile": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint)]),
     "lurk_point_sum": (_i, [_i, _vp, _sz, _i, _vp]),
     "lurk_synthetic_bases": (_i, [_i, C.c_uint64, _sz, _i, _vp]),
+    "lurk_ck_size": (_sz, [_sz, _sz, _sz]),
+    "lurk_ck_generate": (_i, [_i, _vp, _sz, _sz, _i, _vp]),
+    "lurk_ck_generate_dev": (_i, [_i, _vp, _sz, _sz, _vp, _vp]),
+    "lurk_ck_generate_range_dev": (_i, [_i, _vp, _sz, _sz, _sz, _vp, _vp]),
+    "lurk_hash_to_curve_batch": (_i, [_i, C.c_char_p, _vp, _sz, _sz, _i, _vp]),
+    "lurk_hash_to_curve_batch_dev": (_i, [_i, C.c_char_p, _vp, _sz, _sz, _vp, _i, _vp]),
+    "lurk_shake256": (_i, [_vp, _sz, _vp, _sz]),
+    "lurk_sumcheck_prove_dev": (_i, [_i, _i, C.POINTER(_vp), _i, _vp, CHALLENGE_FN, _vp, _vp, _vp, _vp, _i, _vp]),
+    "lurk_eq_evals_dev": (_i, [_i, _vp, _i, _vp, _i, _vp]),
+    "lurk_inner_product_dev": (_i, [_i, _vp, _vp, _sz, _vp, _i, _vp]),
+    "lurk_ipa_fold_scalars_dev": (_i, [_i, _vp, _sz, _vp, _vp, _i, _vp]),
+    "lurk_ipa_fold_bases_dev": (_i, [_i, _vp, _sz, _vp, _vp, _i, _vp]),
+    "lurk_ipa_prove_dev": (_i, [_i, _vp, _vp, _vp, _vp, _i, CHALLENGE_FN, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "lurk_axpy_dev": (_i, [_i, _vp, _vp, _vp, _sz, _vp, _vp]),
     "lurk_spmv_csr_dev": (_i, [_i, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "lurk_cross_term_dev": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),

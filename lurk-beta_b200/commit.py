@@ -34,6 +34,19 @@ class CommitmentKey:
         _capi.check(_capi.lib().lurk_msm_ctx_create_dev(curve_id, C.c_void_p(d_bases_ptr), n, C.byref(self._ctx)))
         return self
 
+    @classmethod
+    def setup(cls, curve_id, label, n, first=0):
+        """Arecibo `CommitmentKey::setup(label, n)` = `DlogGroup::from_label` (public_params, src/proof/nova.rs:196-216): the
+        key is generated on the GPU straight into the device buffer the commitment context reads (it never visits the host).
+        first > 0: points first .. first + n - 1 of the key (a rank's slice of a sharded key)."""
+        import torch
+        buf = torch.empty(max(n, 1) * 64, dtype=torch.uint8, device="cuda")
+        label = bytes(label)
+        _capi.check(_capi.lib().lurk_ck_generate_range_dev(curve_id, label, len(label), first, n, C.c_void_p(buf.data_ptr()), None))
+        self = cls.from_device(curve_id, buf.data_ptr(), n)
+        self._bases = buf            # keeps the borrowed device memory alive
+        return self
+
     def commit(self, scalars, fmt=_capi.FMT_CANONICAL):
         """scalars: uint8 array n*32 (host) -> 96-byte point x|y|z (z = 1, or all zero for the identity)"""
         scalars = np.ascontiguousarray(scalars, dtype=np.uint8).reshape(-1)
@@ -94,6 +107,37 @@ def synthetic_bases(curve_id, n, start=0, fmt=_capi.FMT_CANONICAL):
     out = np.zeros(n * 64, dtype=np.uint8)
     _capi.check(_capi.lib().lurk_synthetic_bases(curve_id, start, n, fmt, _capi.np_ptr(out)))
     return out
+
+
+def ck_size(num_cons, num_vars, ck_floor=0):
+    """R1CSShape::commitment_key: next_power_of_two(max(num_cons, num_vars, ck_floor)) bases"""
+    return int(_capi.lib().lurk_ck_size(num_cons, num_vars, ck_floor))
+
+
+def from_label(curve_id, label, n, fmt=_capi.FMT_CANONICAL):
+    """DlogGroup::from_label(label, n) as a host buffer of n*64 bytes (affine x|y, identity = (0, 0))"""
+    out = np.zeros(n * 64, dtype=np.uint8)
+    label = bytes(label)
+    _capi.check(_capi.lib().lurk_ck_generate(curve_id, label, len(label), n, fmt, _capi.np_ptr(out)))
+    return out
+
+
+def hash_to_curve_batch(curve_id, domain_prefix, messages, msg_len, fmt=_capi.FMT_CANONICAL):
+    """Curve::hash_to_curve(domain_prefix)(m) for every msg_len-byte message of the buffer -> n*64 bytes"""
+    messages = np.ascontiguousarray(messages, dtype=np.uint8).reshape(-1)
+    n = messages.size // msg_len if msg_len else 0
+    out = np.zeros(n * 64, dtype=np.uint8)
+    _capi.check(_capi.lib().lurk_hash_to_curve_batch(curve_id, domain_prefix.encode(), _capi.np_ptr(messages), msg_len, n, fmt,
+                                                     _capi.np_ptr(out)))
+    return out
+
+
+def shake256(data, out_len):
+    """host-side SHAKE256 of the library (the XOF behind from_label)"""
+    data = bytes(data)
+    out = np.zeros(out_len, dtype=np.uint8)
+    _capi.check(_capi.lib().lurk_shake256(data, len(data), _capi.np_ptr(out), out_len))
+    return out.tobytes()
 
 
 def point_sum(curve_id, points, fmt=_capi.FMT_CANONICAL):

@@ -213,6 +213,37 @@ def dag():
         emit(kernel="lurk_dag_hash (host buffers, end to end)", shape=label, nodes=n, ms=round(dt * 1e3, 2), knodes_per_s=round(n / dt / 1e3, 1))
 
 
+def ck_generate(logn=21):
+    """N3: commitment-key generation (DlogGroup::from_label): the map kernel alone on resident uniform bytes, the whole call
+    (SHAKE256 on one host thread pipelined against the kernel), and the CPU oracle (pure Python, one core) on a small sample."""
+    import ctypes as C
+    import hashlib
+    n = 1 << logn
+    stream = np.frombuffer(hashlib.shake_256(b"ck").digest(32 * n), dtype=np.uint8)
+    d_msgs = torch.from_numpy(stream.copy()).cuda()
+    out = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    for curve, cname, exps in ((0, "bn254_g1", "1 batched inversion + 6 square-root passes (s = 1) + 1 inversion"),
+                               (1, "grumpkin", "same with s = 28 Tonelli-Shanks"), (2, "pallas", "1 + 4 square-root passes (s = 32) + isogeny + 1"),
+                               (3, "vesta", "as pallas")):
+        best, med = dev_time(lambda: chk(lib.lurk_hash_to_curve_batch_dev(curve, b"from_uniform_bytes", d_msgs.data_ptr(), 32, n, out.data_ptr(), 1, None)),
+                             reps=3, warm=1)
+        t0 = time.perf_counter()
+        chk(lib.lurk_ck_generate_dev(curve, b"ck", 2, n, C.c_void_p(out.data_ptr()), None))
+        torch.cuda.synchronize()
+        whole = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        hashlib.shake_256(b"ck").digest(32 * n)
+        xof = time.perf_counter() - t0
+        from oracle import h2c   # checker / CPU baseline only
+        t0 = time.perf_counter()
+        h2c.from_label(curve, b"ck", 256)
+        orc = (time.perf_counter() - t0) / 256
+        emit(config=f"N3: from_label, 2^{logn} points", curve=cname, n=n, kernel_ms=round(med, 2), mpoints_per_s=round(n / med / 1e3, 2),
+             whole_call_ms=round(whole * 1e3, 1), hashlib_xof_ms=round(xof * 1e3, 1), work=exps,
+             algorithmic_gb_s=round(n * 96 / med / 1e6, 2), hbm_frac=round(n * 96 / med / 1e6 / PEAK, 5),
+             cpu_oracle_python_us_per_point=round(orc * 1e6, 1), bound="FMA-heavy (IMAD.WIDE) pipe: fixed-exponent exponentiations")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="all")
@@ -228,3 +259,5 @@ if __name__ == "__main__":
         hbm_kernels()
     if a.only in ("all", "dag"):
         dag()
+    if a.only in ("all", "ckgen"):
+        ck_generate(min(a.logn, 21))
