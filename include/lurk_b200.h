@@ -146,6 +146,8 @@ int lurk_msm_ctx_create(int curve_id, const uint8_t *bases_affine, size_t n, int
 /* bases already on the current device (n * 64 bytes, Montgomery); the context borrows the pointer */
 int lurk_msm_ctx_create_dev(int curve_id, const void *d_bases_mont, size_t n, lurk_msm_ctx **out);
 void lurk_msm_ctx_destroy(lurk_msm_ctx *ctx);
+/* curve and number of bases of a context (either output may be NULL) */
+int lurk_msm_ctx_info(lurk_msm_ctx *ctx, int *curve_id, size_t *n);
 /* sum_{i<n} scalars[i] * bases[i], n <= size of the key */
 int lurk_msm_ctx_run(lurk_msm_ctx *ctx, const uint8_t *scalars, size_t n, int fmt, uint8_t out_xyz[96]);
 int lurk_msm_ctx_run_dev(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, uint8_t out_xyz[96],
@@ -202,6 +204,11 @@ int lurk_hash_to_curve_batch(int curve_id, const char *domain_prefix, const uint
                              uint8_t *points_out);
 int lurk_hash_to_curve_batch_dev(int curve_id, const char *domain_prefix, const void *d_messages, size_t msg_len, size_t n,
                                  void *d_points, int fmt, void *stream);
+/* Powers-of-tau key of the KZG engine (Arecibo hyperkzg CommitmentKey::setup -> UniversalKZGParam::gen_srs_for_testing; the
+ * primary circuit's engine on BN256, src/proof/nova.rs:65-71): d_bases_mont[i] = beta^i * g for i < n, affine Montgomery, by
+ * fixed-base windows of g.  g (64 bytes affine) and beta (32 bytes, scalar field) in `fmt`; how the reference derives them from
+ * the label (a seeded RNG) and the verifier key's G2 side stay on the caller's CPU. */
+int lurk_ck_powers_dev(int curve_id, const uint8_t g[64], const uint8_t beta[32], size_t n, void *d_bases_mont, int fmt, void *stream);
 /* SHAKE256(in) -> out_len bytes (FIPS 202).  Host only (works without a GPU); the XOF behind from_label. */
 int lurk_shake256(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len);
 
@@ -242,6 +249,15 @@ int lurk_ipa_fold_bases_dev(int curve_id, void *d_bases_mont, size_t n, const ui
 int lurk_ipa_prove_dev(int curve_id, void *d_bases_mont, const uint8_t ck_c[64], void *d_a, void *d_b, int log_n,
                        lurk_challenge_fn challenge, void *user, uint8_t *L_out, uint8_t *R_out, uint8_t a_final[32], uint8_t b_final[32],
                        int fmt, void *stream);
+/* provider::hyperkzg::EvaluationEngine::prove (the opening argument of the primary BN256 circuit, EE1 in src/proof/nova.rs:65-71):
+ * d_poly = 2^num_vars evaluations (Montgomery, not modified), point = num_vars elements (host, `fmt`), ck = a context on the KZG key
+ * (>= 2^num_vars bases).  Phase 1: P_{i+1}[j] = P_i[2j] + x_{l-1-i} (P_i[2j+1] - P_i[2j]) and com_i = commit(P_i), i = 1..l-1;
+ * challenge(round 0, com) -> r; u = (r, -r, r^2); v[t][j] = P_j(u_t); challenge(round 1, v) -> q; B = sum_j q^j P_j;
+ * w_t = commit(B(X) / (X - u_t)); challenge(round 2, w) is called for the transcript's sake.
+ * com_out: (num_vars - 1) x 96; w_out: 3 x 96; v_out: 3 x num_vars x 32 (v[t][j] at (t * num_vars + j)). */
+int lurk_hyperkzg_prove_dev(int curve_id, lurk_msm_ctx *ck, const void *d_poly, const uint8_t *point, int num_vars,
+                            lurk_challenge_fn challenge, void *user, uint8_t *com_out, uint8_t *w_out, uint8_t *v_out, int fmt,
+                            void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * S5  Fold helpers on device-resident vectors (Arecibo NIFS::prove / R1CSShape::commit_T /

@@ -47,6 +47,19 @@ class CommitmentKey:
         self._bases = buf            # keeps the borrowed device memory alive
         return self
 
+    @classmethod
+    def powers_of_tau(cls, curve_id, g, beta, n):
+        """the KZG engine's key (Arecibo hyperkzg CommitmentKey::setup -> gen_srs_for_testing): beta^i g for i < n, generated on the
+        GPU into the buffer the context reads.  g: (x, y) ints, beta: int."""
+        import torch
+        buf = torch.empty(max(n, 1) * 64, dtype=torch.uint8, device="cuda")
+        gb = np.frombuffer(int(g[0]).to_bytes(32, "little") + int(g[1]).to_bytes(32, "little"), dtype=np.uint8).copy()
+        bb = np.frombuffer(int(beta).to_bytes(32, "little"), dtype=np.uint8).copy()
+        _capi.check(_capi.lib().lurk_ck_powers_dev(curve_id, _capi.np_ptr(gb), _capi.np_ptr(bb), n, C.c_void_p(buf.data_ptr()), _capi.FMT_CANONICAL, None))
+        self = cls.from_device(curve_id, buf.data_ptr(), n)
+        self._bases = buf
+        return self
+
     def commit(self, scalars, fmt=_capi.FMT_CANONICAL):
         """scalars: uint8 array n*32 (host) -> 96-byte point x|y|z (z = 1, or all zero for the identity)"""
         scalars = np.ascontiguousarray(scalars, dtype=np.uint8).reshape(-1)

@@ -55,6 +55,13 @@ int lurk_msm_ctx_last_profile(lurk_msm_ctx *ctx, float *accumulate_ms, unsigned 
     return LURK_OK;
 }
 
+int lurk_msm_ctx_info(lurk_msm_ctx *ctx, int *curve_id, size_t *n) {
+    if (!ctx) { set_error("null context"); return LURK_ERR_ARG; }
+    if (curve_id) *curve_id = ctx->curve_id;
+    if (n) *n = ctx->n;
+    return LURK_OK;
+}
+
 void lurk_msm_ctx_destroy(lurk_msm_ctx *ctx) {
     if (!ctx) return;
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }

@@ -108,3 +108,29 @@ def ipa_prove(curve_id, d_bases_ptr, ck_c, d_a_ptr, d_b_ptr, log_n, challenge, s
             out.append((int.from_bytes(b[:32], "little"), int.from_bytes(b[32:64], "little")) if z else None)
         return out
     return pts(Ls), pts(Rs), int.from_bytes(af.tobytes(), "little"), int.from_bytes(bf.tobytes(), "little")
+
+
+def hyperkzg_prove(curve_id, ck, d_poly_ptr, point, challenge, stream=0):
+    """provider::hyperkzg::EvaluationEngine::prove.  ck: a CommitmentKey on the KZG key; point: ints.  challenge(round, message) -> int
+    with round 0 = commitments, 1 = evaluations, 2 = witness commitments.  Returns (com points, v [3][l] ints, w points)."""
+    l = len(point)
+    pt = np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in point), dtype=np.uint8).copy()
+    com = np.zeros(max(1, l - 1) * 96, dtype=np.uint8)
+    w = np.zeros(3 * 96, dtype=np.uint8)
+    v = np.zeros(3 * l * 32, dtype=np.uint8)
+    errors = []
+    cb = _callback(challenge, errors)
+    rc = _capi.lib().lurk_hyperkzg_prove_dev(curve_id, ck._ctx, C.c_void_p(d_poly_ptr), _capi.np_ptr(pt), l, cb, None, _capi.np_ptr(com),
+                                             _capi.np_ptr(w), _capi.np_ptr(v), _capi.FMT_CANONICAL, C.c_void_p(stream))
+    if errors:
+        raise errors[0]
+    _capi.check(rc)
+
+    def pts(buf, k):
+        out = []
+        for i in range(k):
+            b = buf[96 * i:96 * i + 96].tobytes()
+            out.append((int.from_bytes(b[:32], "little"), int.from_bytes(b[32:64], "little")) if int.from_bytes(b[64:], "little") else None)
+        return out
+    vi = _ints(v)
+    return pts(com, l - 1), [vi[t * l:(t + 1) * l] for t in range(3)], pts(w, 3)
