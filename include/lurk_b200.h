@@ -242,11 +242,14 @@ int lurk_inner_product_dev(int field_id, const void *d_a, const void *d_b, size_
  * (CommitmentKey::fold; bases affine Montgomery; x, y host scalars in `fmt`). */
 int lurk_ipa_fold_scalars_dev(int field_id, void *d_a, size_t n, const uint8_t x[32], const uint8_t y[32], int fmt, void *stream);
 int lurk_ipa_fold_bases_dev(int curve_id, void *d_bases_mont, size_t n, const uint8_t x[32], const uint8_t y[32], int fmt, void *stream);
-/* All log_n rounds of InnerProductArgument::prove on device-resident a, b (scalars, Montgomery) and key G (2^log_n affine points,
- * Montgomery), all three consumed: per round c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo>, L = commit(a_lo; G_hi) + c_L ck_c,
- * R = commit(a_hi; G_lo) + c_R ck_c, r = challenge(L | R), a' = a_lo r + a_hi / r, b' = b_lo / r + b_hi r, G' = G_lo / r + G_hi r.
- * ck_c: the (already scaled) base for the inner-product value, 64 bytes affine in `fmt`.  L_out / R_out: log_n x 96 bytes. */
-int lurk_ipa_prove_dev(int curve_id, void *d_bases_mont, const uint8_t ck_c[64], void *d_a, void *d_b, int log_n,
+/* All log_n rounds of InnerProductArgument::prove on device-resident a, b (2^log_n scalars each, Montgomery, consumed) under the
+ * key of context `ck` (>= 2^log_n bases; NOT consumed): per round c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo>,
+ * L = commit(a_lo; G_hi) + c_L ck_c, R = commit(a_hi; G_lo) + c_R ck_c, r = challenge(L | R), a' = a_lo r + a_hi / r,
+ * b' = b_lo / r + b_hi r, G' = G_lo / r + G_hi r.  The folded key G' is never materialised: the prover only needs commitments under
+ * it, and those are Pippenger passes over the original key with scalars weighted by the products of the earlier challenges
+ * (lurk_ipa_fold_bases_dev is the explicit CommitmentKey::fold for callers that want G').  ck_c: the (already scaled) base for the
+ * inner-product value, 64 bytes affine in `fmt`.  L_out / R_out: log_n x 96 bytes. */
+int lurk_ipa_prove_dev(int curve_id, lurk_msm_ctx *ck, const uint8_t ck_c[64], void *d_a, void *d_b, int log_n,
                        lurk_challenge_fn challenge, void *user, uint8_t *L_out, uint8_t *R_out, uint8_t a_final[32], uint8_t b_final[32],
                        int fmt, void *stream);
 /* provider::hyperkzg::EvaluationEngine::prove (the opening argument of the primary BN256 circuit, EE1 in src/proof/nova.rs:65-71):

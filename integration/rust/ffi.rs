@@ -77,6 +77,33 @@ extern "C" {
     pub fn lurk_fold_ctx_collect(ctx: *mut lurk_fold_ctx, b: c_int, out: *mut lurk_fold_result, fmt: c_int) -> c_int;
     pub fn lurk_fold_ctx_check_running(ctx: *mut lurk_fold_ctx, bad_rows: *mut u64, comm_w_ok: *mut c_int, comm_e_ok: *mut c_int) -> c_int;
     pub fn lurk_fold_ctx_stats(ctx: *mut lurk_fold_ctx, la: *mut c_uint, lb: *mut c_uint, acc_w_ms: *mut f32, acc_t_ms: *mut f32) -> c_int;
+    // N3 -- public_params -> CommitmentKey::setup (src/proof/nova.rs:196-216): from_label (Pedersen engines), powers of tau (HyperKZG)
+    pub fn lurk_ck_size(num_cons: usize, num_vars: usize, ck_floor: usize) -> usize;
+    pub fn lurk_ck_generate(curve_id: c_int, label: *const u8, label_len: usize, n: usize, fmt: c_int, bases_out: *mut u8) -> c_int;
+    pub fn lurk_ck_generate_dev(curve_id: c_int, label: *const u8, label_len: usize, n: usize, d_bases: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn lurk_ck_generate_range_dev(curve_id: c_int, label: *const u8, label_len: usize, first: usize, n: usize, d_bases: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn lurk_ck_powers_dev(curve_id: c_int, g: *const u8, beta: *const u8, n: usize, d_bases: *mut c_void, fmt: c_int, stream: *mut c_void) -> c_int;
+    pub fn lurk_msm_ctx_create_dev(curve_id: c_int, d_bases: *const c_void, n: usize, out: *mut *mut lurk_msm_ctx) -> c_int;
+    // N4 -- compress (src/proof/nova.rs:341-356): the loops of RelaxedR1CSSNARK::prove / EvaluationEngine::prove; the transcript is the callback
+    pub fn lurk_sumcheck_prove_dev(field_id: c_int, kind: c_int, d_polys: *const *mut c_void, num_rounds: c_int, claim: *const u8, challenge: lurk_challenge_fn,
+                                   user: *mut c_void, round_evals: *mut u8, challenges: *mut u8, final_evals: *mut u8, fmt: c_int, stream: *mut c_void) -> c_int;
+    pub fn lurk_eq_evals_dev(field_id: c_int, tau: *const u8, num_vars: c_int, d_out: *mut c_void, fmt: c_int, stream: *mut c_void) -> c_int;
+    pub fn lurk_inner_product_dev(field_id: c_int, d_a: *const c_void, d_b: *const c_void, n: usize, out: *mut u8, fmt: c_int, stream: *mut c_void) -> c_int;
+    pub fn lurk_ipa_prove_dev(curve_id: c_int, ck: *mut lurk_msm_ctx, ck_c: *const u8, d_a: *mut c_void, d_b: *mut c_void, log_n: c_int, challenge: lurk_challenge_fn,
+                              user: *mut c_void, l_out: *mut u8, r_out: *mut u8, a_final: *mut u8, b_final: *mut u8, fmt: c_int, stream: *mut c_void) -> c_int;
+    pub fn lurk_hyperkzg_prove_dev(curve_id: c_int, ck: *mut lurk_msm_ctx, d_poly: *const c_void, point: *const u8, num_vars: c_int, challenge: lurk_challenge_fn,
+                                   user: *mut c_void, com_out: *mut u8, w_out: *mut u8, v_out: *mut u8, fmt: c_int, stream: *mut c_void) -> c_int;
+}
+/// `int (*)(void *user, int round, const uint8_t *message, size_t message_len, uint8_t challenge_out[32])`: the Fiat-Shamir transcript stays in
+/// Rust.  A closure is passed as `user` and trampolined, e.g. for SumcheckProof::prove_*:
+/// `|round, msg| { transcript.absorb(b"p", &UniPoly::from_evals(&elems(msg)).compress()); transcript.squeeze(b"c") }`.
+pub type lurk_challenge_fn = unsafe extern "C" fn(user: *mut c_void, round: c_int, message: *const u8, message_len: usize, challenge_out: *mut u8) -> c_int;
+pub unsafe extern "C" fn challenge_trampoline<F: FnMut(i32, &[u8]) -> Option<[u8; 32]>>(user: *mut c_void, round: c_int, message: *const u8, len: usize, out: *mut u8) -> c_int {
+    let f = &mut *(user as *mut F);
+    match f(round, std::slice::from_raw_parts(message, len)) {
+        Some(r) => { std::ptr::copy_nonoverlapping(r.as_ptr(), out, 32); 0 }
+        None => 1,
+    }
 }
 
 #[derive(Debug)]

@@ -41,7 +41,7 @@ struct ScArgs {
 };
 
 template <class F, int KIND, bool BIND>
-__global__ void __launch_bounds__(256) sc_round_kernel(const __grid_constant__ ScArgs<F> a) {
+__global__ void __launch_bounds__(256, 2) sc_round_kernel(const __grid_constant__ ScArgs<F> a) {
     constexpr int K = ScShape<KIND>::POLYS, E = ScShape<KIND>::EVALS;
     F acc[E];
 #pragma unroll
@@ -133,27 +133,46 @@ __global__ void __launch_bounds__(128) ipa_fold_bases_kernel(Affine<F> *g, size_
 }
 
 // ------------------------------------------------------------------------------------------------ host-side helpers
-// scratch of one prover call: per-CTA partials, the ticket counter, the result slots and their pinned mirror
+// Scratch of the reductions: per-CTA partials, the ticket counter, the result slots and their pinned mirror.  One per host thread
+// and device, kept for the life of the thread: allocating (and above all freeing) device / pinned memory inside every call would
+// synchronise the whole device each time.  Every field element is 32 bytes, so the pool is type-agnostic.
+struct ScPool {
+    void *dev = nullptr, *pinned = nullptr;
+    int device = -1;
+    ~ScPool() { if (dev) cudaFree(dev); if (pinned) cudaFreeHost(pinned); }
+};
+static ScPool &sc_pool() {
+    static thread_local ScPool pool;
+    return pool;
+}
 template <class F>
 struct ScScratch {
-    DevBuf dev;
-    void *pinned = nullptr;
     F *partial = nullptr, *result = nullptr;
     unsigned *counter = nullptr;
-    ~ScScratch() { if (pinned) cudaFreeHost(pinned); }
+    void *pinned = nullptr;
     int init(cudaStream_t s) {
+        ScPool &pool = sc_pool();
         const size_t cap = (size_t)sm_count() * 4;
-        LURK_TRY(dev.alloc(sizeof(F) * (cap * 3 + 8) + 64));
-        partial = dev.as<F>();
-        result = partial + cap * 3;
-        counter = reinterpret_cast<unsigned *>(result + 8);
-        LURK_CUDA_TRY(cudaMemsetAsync(counter, 0, 64, s));
-        LURK_CUDA_TRY(cudaHostAlloc(&pinned, sizeof(F) * 8, cudaHostAllocDefault));
+        int dev = -1;
+        LURK_CUDA_TRY(cudaGetDevice(&dev));
+        if (pool.device != dev) {
+            if (pool.dev) { cudaFree(pool.dev); pool.dev = nullptr; }
+            if (pool.pinned) { cudaFreeHost(pool.pinned); pool.pinned = nullptr; }
+            LURK_CUDA_TRY(cudaMalloc(&pool.dev, 32 * (cap * 3 + 8) + 64));
+            LURK_CUDA_TRY(cudaHostAlloc(&pool.pinned, 32 * 8, cudaHostAllocDefault));
+            pool.device = dev;
+        }
+        partial = static_cast<F *>(pool.dev);
+        counter = reinterpret_cast<unsigned *>(partial + cap * 3 + 8);
+        pinned = pool.pinned;
+        // the result slots ARE the pinned host buffer (unified addressing: the last CTA stores <= 128 bytes across PCIe), so a round
+        // costs one launch + one stream synchronisation and no copy
+        result = static_cast<F *>(pool.pinned);
+        LURK_CUDA_TRY(cudaMemsetAsync(counter, 0, 64, s));     // a kernel that died mid-way must not poison the next call
         return LURK_OK;
     }
-    // copies result[0..k) to the host and waits
+    // waits for the kernel that wrote result[0..k)
     int fetch(int k, F *out, cudaStream_t s) {
-        LURK_CUDA_TRY(cudaMemcpyAsync(pinned, result, sizeof(F) * k, cudaMemcpyDeviceToHost, s));
         LURK_CUDA_TRY(cudaStreamSynchronize(s));
         memcpy(out, pinned, sizeof(F) * k);
         return LURK_OK;
@@ -269,49 +288,108 @@ static void point_to_bytes_fmt(const XYZZ<Fb> &p, int fmt, uint8_t out[96]) {
     memcpy(out, a.x.v, 32); memcpy(out + 32, a.y.v, 32); memcpy(out + 64, one.v, 32);
 }
 
-// [k] P on the host (k a canonical integer): the c_L * ck_c term of an IPA round
+// Fixed-base multiplication of ck_c on the host (the c_L ck_c / c_R ck_c terms, 2 per round): 4-bit windows, 64 mixed additions
+// per product instead of a 254-step double-and-add.
 template <class Fb>
-static XYZZ<Fb> host_scalar_mul(const Affine<Fb> &p, const uint32_t k[8]) {
-    XYZZ<Fb> acc = XYZZ<Fb>::identity();
-    for (int i = 255; i >= 0; i--) {
-        acc = acc.dbl();
-        if ((k[i >> 5] >> (i & 31)) & 1) acc.add_affine(p);
+struct HostFixedBase {
+    std::vector<Affine<Fb>> table;     // table[w * 15 + d - 1] = d 16^w P
+    explicit HostFixedBase(const Affine<Fb> &p) : table(64 * 15) {
+        std::vector<XYZZ<Fb>> pts(64 * 15);
+        Affine<Fb> base = p;
+        for (int w = 0; w < 64; w++) {
+            XYZZ<Fb> acc = XYZZ<Fb>::identity();
+            for (int d = 1; d <= 15; d++) { acc.add_affine(base); pts[w * 15 + d - 1] = acc; }
+            XYZZ<Fb> nb = acc;
+            nb.add_affine(base);
+            base = nb.to_affine();
+        }
+        std::vector<Fb> pref(pts.size());
+        Fb run = Fb::one();
+        for (size_t i = 0; i < pts.size(); i++) { pref[i] = run; if (!pts[i].is_identity()) run = run * pts[i].zzz; }
+        Fb inv = run.inv();
+        for (size_t i = pts.size(); i-- > 0;) {
+            if (pts[i].is_identity()) { table[i].x = Fb::zero(); table[i].y = Fb::zero(); continue; }
+            const Fb zi = inv * pref[i];
+            inv = inv * pts[i].zzz;
+            const Fb zz_inv = (zi * pts[i].zz).sqr();
+            table[i].x = pts[i].x * zz_inv;
+            table[i].y = pts[i].y * zi;
+        }
     }
-    return acc;
+    XYZZ<Fb> mul(const uint32_t k[8]) const {       // k canonical
+        XYZZ<Fb> acc = XYZZ<Fb>::identity();
+        for (int w = 0; w < 64; w++) {
+            const uint32_t d = (k[w >> 3] >> (4 * (w & 7))) & 15u;
+            if (d) acc.add_affine(table[w * 15 + d - 1]);
+        }
+        return acc;
+    }
+};
+
+// The prover never needs the folded key itself, only commitments under it: with W_j[idx] = prod_{k < j} (bit_k(idx) ? r_k : 1 / r_k)
+// (bit_k = the k-th bit of idx from the top) the folded key of round j is G_j[i] = sum_{idx = i mod m} W_j[idx] G[idx], m = n / 2^j, so
+//     L_j = <a_lo, G_j,hi> = sum_{idx : idx mod m >= m/2} W_j[idx] a_j[idx mod m - m/2] G[idx]      (R_j alike on the low halves)
+// -- one Pippenger pass over the ORIGINAL key per commitment (the bucket sort drops the zero half) instead of m / 2 latency-bound
+// 254-bit double-scalar multiplications per round; the key is not consumed and a fixed-base table of it can be reused.
+template <class F>
+__global__ void __launch_bounds__(256) ipa_weighted_kernel(const F *__restrict__ w, const F *__restrict__ a, size_t n, size_t m, F *__restrict__ sl, F *__restrict__ sr) {
+    const size_t half = m / 2;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = idx & (m - 1);
+        const F wi = load_fe<F>(w + idx);
+        if (i >= half) { store_fe(sl + idx, wi * load_fe<F>(a + (i - half))); store_fe(sr + idx, F::zero()); }
+        else { store_fe(sr + idx, wi * load_fe<F>(a + (i + half))); store_fe(sl + idx, F::zero()); }
+    }
+}
+// W_{j+1}[idx] = W_j[idx] * (idx mod m >= m/2 ? r : 1/r)
+template <class F>
+__global__ void __launch_bounds__(256) ipa_weights_update_kernel(F *w, size_t n, size_t m, F r, F r_inv) {
+    const size_t half = m / 2;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x)
+        store_fe(w + idx, load_fe<F>(w + idx) * (((idx & (m - 1)) >= half) ? r : r_inv));
+}
+template <class F>
+__global__ void __launch_bounds__(256) fill_one_kernel(F *w, size_t n) {
+    const F one = F::one();
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) store_fe(w + idx, one);
 }
 
 template <class C>
-static int ipa_prove(void *d_G, const uint8_t *gc_bytes, void *d_a, void *d_b, int log_n, lurk_challenge_fn challenge, void *user,
+static int ipa_prove(lurk_msm_ctx *ck, const uint8_t *gc_bytes, void *d_a, void *d_b, int log_n, lurk_challenge_fn challenge, void *user,
                      uint8_t *L_out, uint8_t *R_out, uint8_t *a_final, uint8_t *b_final, int fmt, cudaStream_t s) {
     using Fb = typename C::Base;
     using Fs = typename C::Scalar;
     Affine<Fb> gc;
     if (!fe_in(gc_bytes, fmt, gc.x) || !fe_in(gc_bytes + 32, fmt, gc.y)) { set_error("ck_c is not reduced"); return LURK_ERR_RANGE; }
+    const HostFixedBase<Fb> gc_mul(gc);
     ScScratch<Fs> sc;
     LURK_TRY(sc.init(s));
     Fs *a = static_cast<Fs *>(d_a), *b = static_cast<Fs *>(d_b);
-    Affine<Fb> *G = static_cast<Affine<Fb> *>(d_G);
-    size_t n = (size_t)1 << log_n;
+    const size_t n = (size_t)1 << log_n;
+    DevBuf wbuf;
+    LURK_TRY(wbuf.alloc(3 * n * sizeof(Fs)));
+    Fs *W = wbuf.as<Fs>(), *sl = W + n, *sr = W + 2 * n;
+    fill_one_kernel<Fs><<<sc_grid(n, 256), 256, 0, s>>>(W, n);
+    LURK_CUDA_TRY(cudaGetLastError());
+    size_t m = n;
     for (int round = 0; round < log_n; round++) {
-        const size_t half = n / 2;
+        const size_t half = m / 2;
         Fs cl, cr;
         LURK_TRY(dot_dev<Fs>(a, b + half, half, &cl, sc, s));
         LURK_TRY(dot_dev<Fs>(a + half, b, half, &cr, sc, s));
+        ipa_weighted_kernel<Fs><<<sc_grid(n, 256), 256, 0, s>>>(W, a, n, m, sl, sr);
+        LURK_CUDA_TRY(cudaGetLastError());
         uint8_t lr[192];
         for (int side = 0; side < 2; side++) {
-            // L = <a_lo, G_hi> + c_L ck_c,  R = <a_hi, G_lo> + c_R ck_c
-            lurk_msm_ctx *ctx = nullptr;
-            LURK_TRY(lurk_msm_ctx_create_dev(C::ID, side == 0 ? (void *)(G + half) : (void *)G, half, &ctx));
+            // L = <a_lo, G_hi> + c_L ck_c,  R = <a_hi, G_lo> + c_R ck_c  (G = the folded key of this round, never materialised)
             uint8_t part[96];
-            int rc = lurk_msm_ctx_run_dev(ctx, side == 0 ? (void *)a : (void *)(a + half), half, LURK_FMT_MONTGOMERY, part, s);
-            lurk_msm_ctx_destroy(ctx);
-            LURK_TRY(rc);
+            LURK_TRY(lurk_msm_ctx_run_dev(ck, side == 0 ? sl : sr, n, LURK_FMT_MONTGOMERY, part, s));
             XYZZ<Fb> acc = XYZZ<Fb>::identity();
             Fb z;
             memcpy(z.v, part + 64, 32);
             if (!z.is_zero()) { Affine<Fb> p; memcpy(p.x.v, part, 32); memcpy(p.y.v, part + 32, 32); acc.add_affine(p); }
             const Fs c = (side == 0 ? cl : cr).to_canonical();
-            acc.add(host_scalar_mul(gc, c.v));
+            acc.add(gc_mul.mul(c.v));
             point_to_bytes_fmt(acc, fmt, lr + 96 * side);
         }
         if (L_out) memcpy(L_out + 96 * (size_t)round, lr, 96);
@@ -322,15 +400,12 @@ static int ipa_prove(void *d_G, const uint8_t *gc_bytes, void *d_a, void *d_b, i
         Fs r;
         if (!fe_in(rbytes, fmt, r) || r.is_zero()) { set_error("challenge of round %d is zero or not reduced", round); return LURK_ERR_RANGE; }
         const Fs r_inv = r.inv();
-        // a' = a_lo r + a_hi r^-1;  b' = b_lo r^-1 + b_hi r;  G' = G_lo r^-1 + G_hi r
+        // a' = a_lo r + a_hi r^-1;  b' = b_lo r^-1 + b_hi r;  key weights: low half r^-1, high half r
         ipa_fold_scalars_kernel<Fs><<<sc_grid(half, 256), 256, 0, s>>>(a, half, r, r_inv);
         ipa_fold_scalars_kernel<Fs><<<sc_grid(half, 256), 256, 0, s>>>(b, half, r_inv, r);
-        Scalar256 x, y;
-        const Fs rc_ = r.to_canonical(), ric = r_inv.to_canonical();
-        for (int i = 0; i < 8; i++) { x.w[i] = ric.v[i]; y.w[i] = rc_.v[i]; }
-        ipa_fold_bases_kernel<Fb><<<sc_grid(half, 128), 128, 0, s>>>(G, half, x, y);
+        ipa_weights_update_kernel<Fs><<<sc_grid(n, 256), 256, 0, s>>>(W, n, m, r, r_inv);
         LURK_CUDA_TRY(cudaGetLastError());
-        n = half;
+        m = half;
     }
     Fs fin[2];
     LURK_CUDA_TRY(cudaMemcpyAsync(&fin[0], a, sizeof(Fs), cudaMemcpyDeviceToHost, s));
@@ -422,14 +497,21 @@ int lurk_ipa_fold_bases_dev(int curve_id, void *d_bases_mont, size_t n, const ui
     });
 }
 
-int lurk_ipa_prove_dev(int curve_id, void *d_bases_mont, const uint8_t ck_c[64], void *d_a, void *d_b, int log_n, lurk_challenge_fn challenge,
+int lurk_ipa_prove_dev(int curve_id, lurk_msm_ctx *ck, const uint8_t ck_c[64], void *d_a, void *d_b, int log_n, lurk_challenge_fn challenge,
                        void *user, uint8_t *L_out, uint8_t *R_out, uint8_t a_final[32], uint8_t b_final[32], int fmt, void *stream) {
-    if (!d_bases_mont || !ck_c || !d_a || !d_b || !challenge) { set_error("null argument"); return LURK_ERR_ARG; }
+    if (!ck || !ck_c || !d_a || !d_b || !challenge) { set_error("null argument"); return LURK_ERR_ARG; }
     if (log_n < 0 || log_n > 30) { set_error("bad log_n %d", log_n); return LURK_ERR_ARG; }
     if (fmt != LURK_FMT_CANONICAL && fmt != LURK_FMT_MONTGOMERY) { set_error("bad format %d", fmt); return LURK_ERR_ARG; }
     LURK_TRY(require_gpu());
+    int ck_curve = -1;
+    size_t ck_n = 0;
+    LURK_TRY(lurk_msm_ctx_info(ck, &ck_curve, &ck_n));
+    if (ck_curve != curve_id || ck_n < ((size_t)1 << log_n)) {
+        set_error("commitment key: curve %d with %zu bases, need curve %d with >= 2^%d", ck_curve, ck_n, curve_id, log_n);
+        return LURK_ERR_ARG;
+    }
     return dispatch_curve(curve_id, [&](auto c) {
-        return ipa_prove<decltype(c)>(d_bases_mont, ck_c, d_a, d_b, log_n, challenge, user, L_out, R_out, a_final, b_final, fmt,
+        return ipa_prove<decltype(c)>(ck, ck_c, d_a, d_b, log_n, challenge, user, L_out, R_out, a_final, b_final, fmt,
                                       static_cast<cudaStream_t>(stream));
     });
 }

@@ -84,16 +84,16 @@ def ipa_fold_bases(curve_id, d_bases_ptr, n, x, y, stream=0):
                                                     _capi.FMT_CANONICAL, C.c_void_p(stream)))
 
 
-def ipa_prove(curve_id, d_bases_ptr, ck_c, d_a_ptr, d_b_ptr, log_n, challenge, stream=0):
-    """InnerProductArgument::prove's rounds.  ck_c: (x, y) canonical ints.  Returns (L points, R points, a_final, b_final);
-    points are (x, y) tuples or None for the identity."""
+def ipa_prove(curve_id, ck, ck_c, d_a_ptr, d_b_ptr, log_n, challenge, stream=0):
+    """InnerProductArgument::prove's rounds under the key of CommitmentKey `ck` (not consumed).  ck_c: (x, y) canonical ints.
+    Returns (L points, R points, a_final, b_final); points are (x, y) tuples or None for the identity."""
     gc = np.concatenate([_fe(ck_c[0]), _fe(ck_c[1])])
     Ls = np.zeros(max(1, log_n) * 96, dtype=np.uint8)
     Rs = np.zeros(max(1, log_n) * 96, dtype=np.uint8)
     af, bf = np.zeros(32, dtype=np.uint8), np.zeros(32, dtype=np.uint8)
     errors = []
     cb = _callback(challenge, errors)
-    rc = _capi.lib().lurk_ipa_prove_dev(curve_id, C.c_void_p(d_bases_ptr), _capi.np_ptr(gc), C.c_void_p(d_a_ptr), C.c_void_p(d_b_ptr), log_n, cb,
+    rc = _capi.lib().lurk_ipa_prove_dev(curve_id, ck._ctx, _capi.np_ptr(gc), C.c_void_p(d_a_ptr), C.c_void_p(d_b_ptr), log_n, cb,
                                         None, _capi.np_ptr(Ls), _capi.np_ptr(Rs), _capi.np_ptr(af), _capi.np_ptr(bf), _capi.FMT_CANONICAL,
                                         C.c_void_p(stream))
     if errors:
