@@ -233,6 +233,14 @@ typedef int (*lurk_challenge_fn)(void *user, int round, const uint8_t *message, 
 int lurk_sumcheck_prove_dev(int field_id, int kind, void *const *d_polys, int num_rounds, const uint8_t claim[32],
                             lurk_challenge_fn challenge, void *user, uint8_t *round_evals, uint8_t *challenges, uint8_t *final_evals,
                             int fmt, void *stream);
+/* SumcheckProof::prove_quad_batch / prove_cubic_with_additive_term_batch (BatchedRelaxedR1CSSNARK: SuperNova's `compress`,
+ * src/proof/supernova.rs:293-317): n_instances (<= 60) claims proven together, the round message is sum_i coeffs[i] * s_i(X).
+ * Instance i has 2 or 4 polynomials of 2^num_rounds[i] elements (d_polys instance-major) and joins in round max - num_rounds[i];
+ * before that its round polynomial is the constant 2^(remaining - num_rounds[i] - 1) * claims[i].  coeffs may be NULL (all 1).
+ * round_evals: max_rounds x (degree + 1) x 32; challenges: max_rounds x 32; final_evals: n_instances x (2 | 4) x 32. */
+int lurk_sumcheck_prove_batch_dev(int field_id, int kind, int n_instances, void *const *d_polys, const int *num_rounds,
+                                  const uint8_t *claims, const uint8_t *coeffs, lurk_challenge_fn challenge, void *user,
+                                  uint8_t *round_evals, uint8_t *challenges, uint8_t *final_evals, int fmt, void *stream);
 /* EqPolynomial::new(tau).evals(): d_out[i] = prod_j (bit_j(i) ? tau[j] : 1 - tau[j]), tau[0] <-> the top index bit; 2^num_vars
  * elements in `fmt` (tau: host, num_vars x 32 bytes, same fmt). */
 int lurk_eq_evals_dev(int field_id, const uint8_t *tau, int num_vars, void *d_out, int fmt, void *stream);

@@ -92,6 +92,7 @@ PROTOTYPES = {
     "lurk_hash_to_curve_batch_dev": (_i, [_i, C.c_char_p, _vp, _sz, _sz, _vp, _i, _vp]),
     "lurk_shake256": (_i, [_vp, _sz, _vp, _sz]),
     "lurk_sumcheck_prove_dev": (_i, [_i, _i, C.POINTER(_vp), _i, _vp, CHALLENGE_FN, _vp, _vp, _vp, _vp, _i, _vp]),
+    "lurk_sumcheck_prove_batch_dev": (_i, [_i, _i, _i, C.POINTER(_vp), C.POINTER(_i), _vp, _vp, CHALLENGE_FN, _vp, _vp, _vp, _vp, _i, _vp]),
     "lurk_eq_evals_dev": (_i, [_i, _vp, _i, _vp, _i, _vp]),
     "lurk_inner_product_dev": (_i, [_i, _vp, _vp, _sz, _vp, _i, _vp]),
     "lurk_ipa_fold_scalars_dev": (_i, [_i, _vp, _sz, _vp, _vp, _i, _vp]),

@@ -51,6 +51,31 @@ def sumcheck_prove(field_id, kind, poly_ptrs, num_rounds, claim, challenge, stre
     return [ev[i * deg1:(i + 1) * deg1] for i in range(num_rounds)], _ints(chal)[:num_rounds], _ints(fin)
 
 
+def sumcheck_prove_batch(field_id, kind, instances, claims, coeffs, challenge, stream=0):
+    """SumcheckProof::prove_*_batch.  instances: [(poly_ptrs, num_rounds)], claims / coeffs: ints.
+    Returns (round_evals, challenges, final_evals per instance)."""
+    k, deg1 = (2, 3) if kind == QUAD else (4, 4)
+    n = len(instances)
+    flat = [p for ptrs, _ in instances for p in ptrs]
+    ptrs = (C.c_void_p * (n * k))(*[C.c_void_p(p) for p in flat])
+    nr = (C.c_int * n)(*[r for _, r in instances])
+    mx = max(r for _, r in instances)
+    rounds = np.zeros(max(1, mx) * deg1 * 32, dtype=np.uint8)
+    chal = np.zeros(max(1, mx) * 32, dtype=np.uint8)
+    fin = np.zeros(n * k * 32, dtype=np.uint8)
+    cl = np.concatenate([_fe(c) for c in claims])
+    co = np.concatenate([_fe(c) for c in coeffs])
+    errors = []
+    cb = _callback(challenge, errors)
+    rc = _capi.lib().lurk_sumcheck_prove_batch_dev(field_id, kind, n, ptrs, nr, _capi.np_ptr(cl), _capi.np_ptr(co), cb, None, _capi.np_ptr(rounds),
+                                                   _capi.np_ptr(chal), _capi.np_ptr(fin), _capi.FMT_CANONICAL, C.c_void_p(stream))
+    if errors:
+        raise errors[0]
+    _capi.check(rc)
+    ev, fi = _ints(rounds), _ints(fin)
+    return [ev[i * deg1:(i + 1) * deg1] for i in range(mx)], _ints(chal)[:mx], [fi[i * k:(i + 1) * k] for i in range(n)]
+
+
 def eq_evals(field_id, tau, d_out_ptr, out_fmt=_capi.FMT_MONTGOMERY, stream=0):
     """EqPolynomial::new(tau).evals() into device memory (2^len(tau) elements in out_fmt); tau: ints"""
     R = 1 << 256

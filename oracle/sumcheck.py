@@ -115,6 +115,35 @@ def verify(rounds, rs, claim, degree, p):
     return claim
 
 
+def prove_batch(instances, kind, claims, coeffs, challenge, p):
+    """SumcheckProof::prove_quad_batch / prove_cubic_with_additive_term_batch.  instances: list of polynomial lists (each instance
+    2 or 4 polynomials of 2^nr_i elements).  Returns (rounds, challenges, final evaluations per instance, final claim)."""
+    insts = [[list(P) for P in polys] for polys in instances]
+    nr = [len(polys[0]).bit_length() - 1 for polys in insts]
+    mx = max(nr)
+    e = sum(c * (1 << (mx - n)) * cl for c, n, cl in zip(coeffs, nr, claims)) % p
+    rounds, rs = [], []
+    for rnd in range(mx):
+        remaining = mx - rnd
+        comb = None
+        for i, polys in enumerate(insts):
+            if remaining <= nr[i]:
+                ev = round_evals(polys, kind, p)
+            else:
+                sc = (1 << (remaining - nr[i] - 1)) * claims[i] % p
+                ev = (sc,) * (2 if kind == "quad" else 3)
+            comb = [coeffs[i] * x % p for x in ev] if comb is None else [(a + coeffs[i] * x) % p for a, x in zip(comb, ev)]
+        evals = [comb[0], (e - comb[0]) % p] + comb[1:]
+        r = challenge(rnd, evals) % p
+        rounds.append(evals)
+        rs.append(r)
+        e = uni_eval_from_evals(evals, r, p)
+        for i, polys in enumerate(insts):
+            if remaining <= nr[i]:
+                insts[i] = [bind_top(P, r, p) for P in polys]
+    return rounds, rs, [[P[0] for P in polys] for polys in insts], e
+
+
 # ------------------------------------------------------------------------------------------------ inner-product argument
 def inner_product(a, b, p):
     return sum(x * y for x, y in zip(a, b)) % p

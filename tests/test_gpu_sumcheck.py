@@ -212,3 +212,57 @@ def test_ipa_prove_rounds_and_verifier_relation(L, oracle, spec, curve, log_n):
     # the key is not consumed: committing under it still gives the oracle's commitment
     assert np.array_equal(ck.commit(a_h), oracle.msm(curve, bases[:64 * n], a_h, nthreads=4))
     assert add(mul(a_fin, G[0]), mul(a_fin * b_fin, gc)) == acc
+
+
+@pytest.mark.parametrize("kind", ["quad", "cubic"])
+def test_batched_sumcheck_matches_oracle(L, spec, kind):
+    """SuperNova's batched sum-check: instances of 2^9, 2^4, 2^0, 2^9, 2^1 elements with random coefficients"""
+    field = 0
+    p = spec.FIELD_MODULUS[field]
+    k = 2 if kind == "quad" else 4
+    sizes = [9, 4, 0, 9, 1]
+    bufs = [[random_elements(field, 1 << l, seed=100 * i + j) for j in range(k)] for i, l in enumerate(sizes)]
+    insts = [[ints(b) for b in polys] for polys in bufs]
+    comb = sc.comb_quad if kind == "quad" else sc.comb_cubic
+    claims = [sum(comb(*[P[i] for P in polys], p) for i in range(len(polys[0]))) % p for polys in insts]
+    coeffs = ints(random_elements(field, len(sizes), seed=7))
+    want = sc.prove_batch(insts, kind, claims, coeffs, fs_challenge(p, b"B"), p)
+    dev = [[to_device(L, field, b) for b in polys] for polys in bufs]
+    got = L.spartan.sumcheck_prove_batch(field, L.spartan.QUAD if kind == "quad" else L.spartan.CUBIC,
+                                         [([d.data_ptr() for d in polys], l) for polys, l in zip(dev, sizes)], claims, coeffs, msg_challenge(p, b"B"))
+    assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2]
+    e0 = sum(c * (1 << (9 - l)) * cl for c, l, cl in zip(coeffs, sizes, claims)) % p
+    assert sc.verify(got[0], got[1], e0, 2 if kind == "quad" else 3, p) == sum(c * comb(*f, p) for c, f in zip(coeffs, got[2])) % p
+
+
+def test_provers_from_concurrent_host_threads(L, spec):
+    """the reference calls its prover from rayon workers: four host threads run sum-checks at once (per-thread reduction scratch,
+    callbacks re-entering Python) and every transcript equals the oracle's"""
+    import threading
+    field = 0
+    p = spec.FIELD_MODULUS[field]
+    l = 9
+    results, errors = {}, []
+
+    def work(t):
+        try:
+            bufs = [random_elements(field, 1 << l, seed=1000 * t + i) for i in range(4)]
+            polys = [ints(b) for b in bufs]
+            claim = sum(sc.comb_cubic(*[P[i] for P in polys], p) for i in range(1 << l)) % p
+            dev = [to_device(L, field, b) for b in bufs]
+            for _ in range(3):
+                work_copy = [d.clone() for d in dev]
+                got = L.spartan.sumcheck_prove(field, L.spartan.CUBIC, [d.data_ptr() for d in work_copy], l, claim, msg_challenge(p, bytes([t])))
+            results[t] = (got, sc.prove(polys, "cubic", claim, fs_challenge(p, bytes([t])), p))
+        except Exception as e:       # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for t in range(4):
+        got, want = results[t]
+        assert (got[0], got[1], got[2]) == (want[0], want[1], want[2]), t

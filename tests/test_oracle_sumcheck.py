@@ -131,3 +131,29 @@ def test_product_ipa_fold_arithmetic_against_oracle(sclib, spec, curve):
         assert sclib.sc_test_fold_point(curve, pack(P), pack(Q2), pack([x]), pack([y]), out) == 0
         want = sc.ipa_fold_bases(curve, [P, Q2], x, y)[0]
         assert tuple(unpack(out.raw, 2)) == (want if want is not None else (0, 0))
+
+
+@pytest.mark.parametrize("kind", ["quad", "cubic"])
+def test_oracle_batched_prover_final_check(spec, kind):
+    """batched sum-check over instances of different sizes: the verifier's final check sum_i coeff_i comb(final_i) eq-free form:
+    the last claim equals the combination of the instances' final evaluations, and every instance's final evaluations are its
+    multilinear extensions at the LAST nr_i challenges"""
+    p = spec.FIELD_MODULUS[0]
+    rnd = random.Random(5)
+    k = 2 if kind == "quad" else 4
+    sizes = [5, 3, 0, 5, 1]
+    insts = [[[rnd.randrange(p) for _ in range(1 << l)] for _ in range(k)] for l in sizes]
+    comb = sc.comb_quad if kind == "quad" else sc.comb_cubic
+    claims = [sum(comb(*[P[i] for P in polys], p) for i in range(len(polys[0]))) % p for polys in insts]
+    coeffs = [rnd.randrange(p) for _ in sizes]
+    rounds, rs, finals, last = sc.prove_batch(insts, kind, claims, coeffs, fs_challenge(p, b"b"), p)
+    assert len(rounds) == 5
+    e0 = sum(c * (1 << (5 - l)) * cl for c, l, cl in zip(coeffs, sizes, claims)) % p
+    assert sc.verify(rounds, rs, e0, 2 if kind == "quad" else 3, p) == last
+    assert last == sum(c * comb(*f, p) for c, f in zip(coeffs, finals)) % p
+    for polys, l, f in zip(insts, sizes, finals):
+        assert f == [sc.mle_eval(P, rs[5 - l:], p) for P in polys]
+    # one instance with coefficient 1 is the plain prover
+    single = sc.prove(insts[0], kind, claims[0], fs_challenge(p, b"b"), p)
+    again = sc.prove_batch([insts[0]], kind, [claims[0]], [1], fs_challenge(p, b"b"), p)
+    assert (single[0], single[1], single[2]) == (again[0], again[1], again[2][0])

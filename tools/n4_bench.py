@@ -139,10 +139,13 @@ def main():
                 chk(lib.lurk_ipa_prove_dev(curve, ckk._ctx, L._capi.np_ptr(gc), C.c_void_p(aa.data_ptr()), C.c_void_p(bb.data_ptr()), ll, cb, user,
                                            None, None, None, None, 1, None))
                 return (time.perf_counter() - t0) * 1e3
-            run()
-            ts = sorted(run() for _ in range(3))
-            emit(op="lurk_ipa_prove_dev", curve=cname, log_n=ll, ms=round(ts[1], 2), ms_best=round(ts[0], 2),
-                 note="per round: 2 inner products, 2 Pippenger passes over the fixed key (n/2 non-zero weighted scalars each), folds of a and b, weight update")
+            for fixed in (False, True):
+                if fixed:
+                    ckk.precompute()
+                run()
+                ts = sorted(run() for _ in range(3))
+                emit(op="lurk_ipa_prove_dev", curve=cname, log_n=ll, fixed_base_table=fixed, ms=round(ts[1], 2), ms_best=round(ts[0], 2),
+                     note="per round: 2 inner products, 2 Pippenger passes over the fixed key (n/2 non-zero weighted scalars each), folds of a and b, weight update")
 
     if a.only in ("all", "kzg"):
         curve = 0
@@ -161,10 +164,13 @@ def main():
             t0 = time.perf_counter()
             chk(lib.lurk_hyperkzg_prove_dev(curve, ck._ctx, C.c_void_p(poly.data_ptr()), L._capi.np_ptr(point), l, cb, user, None, None, None, 1, None))
             return (time.perf_counter() - t0) * 1e3
-        run()
-        ts = sorted(run() for _ in range(3))
-        emit(op="lurk_hyperkzg_prove_dev", curve="bn254_g1", log_n=l, ms=round(ts[1], 2), ms_best=round(ts[0], 2),
-             note="l - 1 folds + l - 1 commitments (n/2 .. 2 terms), 3 l evaluations, batched polynomial, 3 witness polynomials + 3 n-term commitments")
+        for fixed in (False, True):
+            if fixed:
+                ck.precompute()
+            run()
+            ts = sorted(run() for _ in range(3))
+            emit(op="lurk_hyperkzg_prove_dev", curve="bn254_g1", log_n=l, fixed_base_table=fixed, ms=round(ts[1], 2), ms_best=round(ts[0], 2),
+                 note="l - 1 folds + l - 1 commitments (n/2 .. 2 terms), 3 l evaluations, batched polynomial, 3 witness polynomials + 3 n-term commitments")
     emit(callbacks=calls.value)
 
 
