@@ -124,6 +124,13 @@ static int ipa_prove(lurk_msm_ctx *ck, const uint8_t *gc_bytes, void *d_a, void 
     Fs *W = wbuf.as<Fs>(), *sl = W + n, *sr = W + 2 * n;
     fill_one_kernel<Fs><<<sc_grid(n, 256), 256, 0, s>>>(W, n);
     LURK_CUDA_TRY(cudaGetLastError());
+    // L and R of a round are independent: the second one runs on a clone of the context (same resident key, own scratch) and a side stream
+    MsmCloneGuard ck_r;
+    LURK_TRY(lurk_msm_ctx_clone(ck, &ck_r.c));
+    StreamGuard s_r;
+    LURK_TRY(s_r.create());
+    EventGuard weighted;
+    LURK_TRY(weighted.create());
     size_t m = n;
     for (int round = 0; round < log_n; round++) {
         const size_t half = m / 2;
@@ -132,11 +139,17 @@ static int ipa_prove(lurk_msm_ctx *ck, const uint8_t *gc_bytes, void *d_a, void 
         LURK_TRY(dot_dev<Fs>(a + half, b, half, &cr, sc, s));
         ipa_weighted_kernel<Fs><<<sc_grid(n, 256), 256, 0, s>>>(W, a, n, m, sl, sr);
         LURK_CUDA_TRY(cudaGetLastError());
+        LURK_CUDA_TRY(cudaEventRecord(weighted.e, s));
+        LURK_CUDA_TRY(cudaStreamWaitEvent(s_r.s, weighted.e, 0));
+        uint8_t parts[2][96];
+        LURK_TRY(lurk_msm_ctx_launch_dev(ck, sl, n, LURK_FMT_MONTGOMERY, s));
+        LURK_TRY(lurk_msm_ctx_launch_dev(ck_r.c, sr, n, LURK_FMT_MONTGOMERY, s_r.s));
+        LURK_TRY(lurk_msm_ctx_finish(ck, parts[0]));
+        LURK_TRY(lurk_msm_ctx_finish(ck_r.c, parts[1]));        // both passes are complete before anything below touches sl / sr / a
         uint8_t lr[192];
         for (int side = 0; side < 2; side++) {
             // L = <a_lo, G_hi> + c_L ck_c,  R = <a_hi, G_lo> + c_R ck_c  (G = the folded key of this round, never materialised)
-            uint8_t part[96];
-            LURK_TRY(lurk_msm_ctx_run_dev(ck, side == 0 ? sl : sr, n, LURK_FMT_MONTGOMERY, part, s));
+            const uint8_t *part = parts[side];
             XYZZ<Fb> acc = XYZZ<Fb>::identity();
             Fb z;
             memcpy(z.v, part + 64, 32);

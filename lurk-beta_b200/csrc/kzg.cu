@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "kzg.cuh"
 #include "reduce.cuh"
+#include "sc_scratch.cuh"
 
 #include <algorithm>
 #include <vector>
@@ -197,20 +198,6 @@ __global__ void kzg_eval_sum_kernel(const F *__restrict__ partial, size_t nchunk
     store_fe(v + t, s);
 }
 
-template <class F>
-static inline void fe_out(const F &x_mont, int fmt, uint8_t *out) {
-    F v = fmt == LURK_FMT_CANONICAL ? x_mont.to_canonical() : x_mont;
-    memcpy(out, v.v, 32);
-}
-template <class F>
-static inline bool fe_in(const uint8_t *in, int fmt, F &x_mont) {
-    F v;
-    memcpy(v.v, in, 32);
-    if (!v.is_reduced()) return false;
-    x_mont = fmt == LURK_FMT_CANONICAL ? F::from_canonical(v) : v;
-    return true;
-}
-
 // lurk_msm_ctx_run_dev takes ONE format for the scalars and the result: the vectors here are Montgomery, the caller may want canonical
 template <class Fb>
 static void points_to_fmt(uint8_t *pts96, int count, int fmt) {
@@ -270,9 +257,29 @@ static int hyperkzg_prove(lurk_msm_ctx *ck, const void *d_poly, const uint8_t *p
         kzg_fold_kernel<F><<<kzg_grid(half, 256), 256, 0, s>>>(polys + kzg_poly_offset(n, i), polys + kzg_poly_offset(n, i + 1), half, x[l - 1 - i]);
     }
     LURK_CUDA_TRY(cudaGetLastError());
+    // the l - 1 commitments are independent and mostly short (latency-bound Pippenger chains): three of them in flight, on the context and
+    // two clones of it (same resident key, own scratch), each on its own stream
+    MsmCloneGuard clone[2];
+    StreamGuard side[2];
+    EventGuard ready;
+    LURK_TRY(ready.create());
+    for (int k = 0; k < 2; k++) { LURK_TRY(lurk_msm_ctx_clone(ck, &clone[k].c)); LURK_TRY(side[k].create()); }
+    lurk_msm_ctx *ctxs[3] = {ck, clone[0].c, clone[1].c};
+    cudaStream_t streams[3] = {s, side[0].s, side[1].s};
+    LURK_CUDA_TRY(cudaEventRecord(ready.e, s));
+    for (int k = 1; k < 3; k++) LURK_CUDA_TRY(cudaStreamWaitEvent(streams[k], ready.e, 0));
     std::vector<uint8_t> com((size_t)std::max(l - 1, 1) * 96);
-    for (int j = 1; j < l; j++)
-        LURK_TRY(lurk_msm_ctx_run_dev(ck, polys + kzg_poly_offset(n, j), n >> j, LURK_FMT_MONTGOMERY, com.data() + 96 * (size_t)(j - 1), s));
+    {
+        int pending[3] = {0, 0, 0};
+        for (int j = 1; j < l; j++) {
+            const int k = j % 3;
+            if (pending[k]) LURK_TRY(lurk_msm_ctx_finish(ctxs[k], com.data() + 96 * (size_t)(pending[k] - 1)));
+            LURK_TRY(lurk_msm_ctx_launch_dev(ctxs[k], polys + kzg_poly_offset(n, j), n >> j, LURK_FMT_MONTGOMERY, streams[k]));
+            pending[k] = j;
+        }
+        for (int k = 0; k < 3; k++)
+            if (pending[k]) LURK_TRY(lurk_msm_ctx_finish(ctxs[k], com.data() + 96 * (size_t)(pending[k] - 1)));
+    }
     points_to_fmt<typename C::Base>(com.data(), l - 1, fmt);
     if (com_out && l > 1) memcpy(com_out, com.data(), (size_t)(l - 1) * 96);
     // Phase 2: r from the commitments; u = (r, -r, r^2)
@@ -329,7 +336,10 @@ static int hyperkzg_prove(lurk_msm_ctx *ck, const void *d_poly, const uint8_t *p
     LURK_CUDA_TRY(cudaGetLastError());
     LURK_TRY(kzg_witness_polys<F>(d_B.as<F>(), n, u, d_h.as<F>(), scan_scratch, s));
     uint8_t w[3 * 96];
-    for (int y = 0; y < 3; y++) LURK_TRY(lurk_msm_ctx_run_dev(ck, d_h.as<F>() + (size_t)y * n, n, LURK_FMT_MONTGOMERY, w + 96 * y, s));
+    LURK_CUDA_TRY(cudaEventRecord(ready.e, s));
+    for (int k = 1; k < 3; k++) LURK_CUDA_TRY(cudaStreamWaitEvent(streams[k], ready.e, 0));
+    for (int y = 0; y < 3; y++) LURK_TRY(lurk_msm_ctx_launch_dev(ctxs[y], d_h.as<F>() + (size_t)y * n, n, LURK_FMT_MONTGOMERY, streams[y]));
+    for (int y = 0; y < 3; y++) LURK_TRY(lurk_msm_ctx_finish(ctxs[y], w + 96 * y));
     points_to_fmt<typename C::Base>(w, 3, fmt);
     if (w_out) memcpy(w_out, w, sizeof w);
     uint8_t ignored[32];

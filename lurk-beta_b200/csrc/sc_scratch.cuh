@@ -5,6 +5,11 @@
 
 namespace lurk {
 
+// RAII for the side streams / cloned commitment contexts that let independent Pippenger passes of one prover call overlap
+struct StreamGuard { cudaStream_t s = nullptr; ~StreamGuard() { if (s) cudaStreamDestroy(s); } int create() { LURK_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return LURK_OK; } };
+struct EventGuard { cudaEvent_t e = nullptr; ~EventGuard() { if (e) cudaEventDestroy(e); } int create() { LURK_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return LURK_OK; } };
+struct MsmCloneGuard { lurk_msm_ctx *c = nullptr; ~MsmCloneGuard() { if (c) lurk_msm_ctx_destroy(c); } };
+
 static inline int sc_grid(size_t n, int block) {
     size_t want = (n + block - 1) / block;
     size_t cap = (size_t)sm_count() * 4;

@@ -135,6 +135,7 @@ static int sumcheck_prove_batch(int n_inst, void *const *d_polys, const int *nr,
     F e = F::zero();
     for (int i = 0; i < n_inst; i++) e += coeff[i] * claim[i] * pow2(max_rounds - nr[i]);
     F r_prev = F::zero();
+    const ScLagrange<F> lagrange(DEG1);
     for (int round = 0; round < max_rounds; round++) {
         const int remaining = max_rounds - round;
         for (int i = 0; i < n_inst; i++) {
@@ -176,7 +177,7 @@ static int sumcheck_prove_batch(int n_inst, void *const *d_polys, const int *nr,
         F r;
         if (!fe_in(rbytes, fmt, r)) { set_error("challenge of round %d is not reduced", round); return LURK_ERR_RANGE; }
         if (challenges) memcpy(challenges + (size_t)round * 32, rbytes, 32);
-        e = sc_interpolate(evals, DEG1, r);
+        e = lagrange.eval(evals, r);
         r_prev = r;
         for (int i = 0; i < n_inst; i++)
             if (remaining <= nr[i]) cur[i] >>= 1;

@@ -37,21 +37,36 @@ LURK_HD void sc_accumulate(const F *lo, const F *hi, F *acc) {
     }
 }
 
-// value at x of the polynomial of degree n - 1 through (0, e[0]), (1, e[1]), ... (n <= 4): UniPoly::from_evals + evaluate
+// value at x of the polynomial of degree n - 1 through (0, e[0]), (1, e[1]), ... (n <= 4): UniPoly::from_evals + evaluate.
+// The Lagrange denominators prod_{j != i} (i - j) are constants of n: ScLagrange inverts them ONCE per prover call -- a Fermat
+// inversion is ~380 host products, and four of them per round were half of a round's host time.
 template <class F>
-LURK_HD F sc_interpolate(const F *e, int n, const F &x) {
-    F total = F::zero();
-    for (int i = 0; i < n; i++) {
-        F num = F::one(), den = F::one();
-        for (int j = 0; j < n; j++) {
-            if (j == i) continue;
-            num = num * (x - F::from_u64((uint64_t)j));
-            den = den * (i > j ? F::from_u64((uint64_t)(i - j)) : F::from_u64((uint64_t)(j - i)).neg());
+struct ScLagrange {
+    int n;
+    F inv_den[4];
+    explicit ScLagrange(int n_) : n(n_) {
+        for (int i = 0; i < n; i++) {
+            F den = F::one();
+            for (int j = 0; j < n; j++) {
+                if (j == i) continue;
+                den = den * (i > j ? F::from_u64((uint64_t)(i - j)) : F::from_u64((uint64_t)(j - i)).neg());
+            }
+            inv_den[i] = den.inv();
         }
-        total += e[i] * num * den.inv();
     }
-    return total;
-}
+    F eval(const F *e, const F &x) const {
+        F total = F::zero();
+        for (int i = 0; i < n; i++) {
+            F num = F::one();
+            for (int j = 0; j < n; j++)
+                if (j != i) num = num * (x - F::from_u64((uint64_t)j));
+            total += e[i] * num * inv_den[i];
+        }
+        return total;
+    }
+};
+template <class F>
+inline F sc_interpolate(const F *e, int n, const F &x) { return ScLagrange<F>(n).eval(e, x); }
 
 // IPA scalar fold: x a[i] + y a[i + n/2] with one reduction
 template <class F>

@@ -171,7 +171,12 @@ def main():
             ts = sorted(run() for _ in range(3))
             emit(op="lurk_hyperkzg_prove_dev", curve="bn254_g1", log_n=l, fixed_base_table=fixed, ms=round(ts[1], 2), ms_best=round(ts[0], 2),
                  note="l - 1 folds + l - 1 commitments (n/2 .. 2 terms), 3 l evaluations, batched polynomial, 3 witness polynomials + 3 n-term commitments")
-    emit(callbacks=calls.value)
+    try:
+        q = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_throttle_reasons.active", "--format=csv,noheader", "-i", "0"],
+                           capture_output=True, text=True, timeout=10).stdout.strip()
+    except Exception as e:
+        q = str(e)
+    emit(callbacks=calls.value, nvidia_smi_after=q)
 
 
 if __name__ == "__main__":
