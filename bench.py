@@ -577,7 +577,9 @@ def run_gpu(args):
     # the dominant kernel with nothing else on the GPU (inside the step it overlaps other streams' kernels)
     iso = []
     wl.ck_t.set_profiling(True)
-    tbuf, tn = wl.ctx.device_buffer(0, wl.L._capi.FOLD_BUF_E1)     # the running error vector: dense, full-width scalars
+    tbuf, tn = wl.ctx.device_buffer(0, wl.L._capi.FOLD_BUF_E1)     # the running error vector: full-width scalars on the rows T touches
+    e_view = wl.ctx.device_view(0, wl.L._capi.FOLD_BUF_E1)[:wl.nT * 32].view(wl.nT, 32)
+    iso_nonzero = int((e_view != 0).any(dim=1).sum().item())       # zero scalars never enter the bucket sort
     for _ in range(5):
         wl.ck_t.launch_device(tbuf, wl.nT, fmt=wl.L.FMT_MONTGOMERY, stream=0)
         wl.ck_t.finish()
@@ -597,7 +599,9 @@ def run_gpu(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         iso_ms = sum(iso) / max(1, len(iso))
         terms = wl.nT
-        achieved = terms * 96 / (iso_ms / 1e3) / 1e9 if iso_ms > 0 else 0.0
+        # algorithmic bytes of THIS launch: 96 B per non-zero term (scalar + base), 32 B per zero scalar (read and dropped)
+        iso_bytes = iso_nonzero * 96 + (terms - iso_nonzero) * 32
+        achieved = iso_bytes / (iso_ms / 1e3) / 1e9 if iso_ms > 0 else 0.0
         launches = sum(x["launches_a"] + x["launches_b"] for x in stats)
         out = {
             "metric": METRIC, "value": round(value, 2), "unit": "iterations/s",
@@ -612,11 +616,12 @@ def run_gpu(args):
                          "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
                          "traffic": ncu_traffic(),
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch in profiles/r2_ncu_full_msm_accumulate_iso_raw.csv (ncu --set full of "
-                                         "this kernel on the same dense 1114100-term vector and c = 20 table, tools/acc_iso.py); Pippenger gathers each 64-byte "
-                                         "window multiple once per window (13 x 64 B + index per term)",
+                                         "this kernel on a DENSE 1114100-term vector and the c = 20 table, tools/acc_iso.py: 2.35 ms, 45.5 GB/s algorithmic); the launch "
+                                         "timed here runs on the running error vector (terms_nonzero of terms) with commit(T)'s c = 16 table; Pippenger gathers each "
+                                         "64-byte window multiple once per window",
                          "avg_launch_ms": round(iso_ms, 4), "avg_launch_ms_overlapped_in_step": {"commit_W": round(st["accumulate_w_ms"], 4),
                                                                                                 "commit_T": round(st["accumulate_t_ms"], 4)},
-                         "algorithmic_bytes_per_launch": int(terms * 96),
+                         "algorithmic_bytes_per_launch": int(iso_bytes), "terms": int(terms), "terms_nonzero": iso_nonzero,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "note": "bound by the FMA-heavy (IMAD.WIDE) pipe (ncu captures in profiles/): ~13 bucket additions x ~1.4e3 IMAD.WIDE "
                                  "per 96 algorithmic bytes; launch time = CUDA events inside the library on the launching stream, kernel run "

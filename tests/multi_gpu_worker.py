@@ -8,7 +8,8 @@ commitments are exchanged inside the challenge kernel over peer memory.  Checked
   * the rank's slice of the folded W / E equals the oracle's slice, u and X agree;
   * check_running() (collective) reports a satisfied relaxed R1CS with consistent commitments;
   * rank 0 also runs the same chain on one GPU (world = 1) and gets identical records;
-  * ShardedCommitmentKey.commit over NCCL equals the oracle's commitment.
+  * ShardedCommitmentKey.commit over NCCL equals the oracle's commitment;
+  * a commitment key generated slice by slice on the ranks' GPUs (N3, lurk_ck_generate_range_dev) commits like the oracle's whole key.
 Exit code 0 = all assertions passed on this rank."""
 import os
 import sys
@@ -135,6 +136,19 @@ def main():
     sk = L.ShardedCommitmentKey(CURVE, bases[lo * 64:hi * 64], n_w)
     got = sk.commit(sc[lo * 32:hi * 32])
     assert np.array_equal(got, oracle.msm(CURVE, bases, sc, nthreads=8)), "ShardedCommitmentKey.commit"
+    # ---- N3 on N GPUs: every rank GENERATES its slice of the reference's key (DlogGroup::from_label, points lo..hi) on its own GPU;
+    # the sharded commitment over the generated slices equals the oracle's commitment over the oracle's restatement of the whole key
+    from oracle import h2c
+    import ctypes as C
+    nk = 96 * world + 5
+    klo, khi = L.shard_bounds(nk, world, rank)
+    mine = L.CommitmentKey.setup(CURVE, b"ck", khi - klo, first=klo)
+    whole = np.frombuffer(h2c.from_label_bytes(CURVE, b"ck", nk), dtype=np.uint8)
+    ksc = T.random_elements(FIELD, nk, seed=78, shape="uniform")
+    part = torch.from_numpy(mine.commit(ksc[klo * 32:khi * 32])).cuda()
+    allp = torch.empty(96 * world, dtype=torch.uint8, device="cuda")
+    dist.all_gather_into_tensor(allp, part)
+    assert np.array_equal(L.point_sum(CURVE, allp.cpu().numpy()), oracle.msm(CURVE, whole, ksc, nthreads=8)), "sharded from_label key"
     dist.barrier()
     print(f"rank {rank}: multi-GPU fold parity ok", flush=True)
     dist.destroy_process_group()
