@@ -159,3 +159,135 @@ def hyperkzg_prove(curve_id, ck, d_poly_ptr, point, challenge, stream=0):
         return out
     vi = _ints(v)
     return pts(com, l - 1), [vi[t * l:(t + 1) * l] for t in range(3)], pts(w, 3)
+
+
+
+# ------------------------------------------------------------------------------------------------ RelaxedR1CSSNARK::prove, the GPU half
+class DeviceCSR:
+    """a CSR matrix resident on the GPU (row_ptr u64, col u32, val Montgomery field elements)"""
+
+    def __init__(self, field_id, rows, row_ptr, col, val_canonical):
+        import torch
+        self.rows = rows
+        self.rp = torch.from_numpy(np.ascontiguousarray(row_ptr, dtype=np.uint64).view(np.int64)).cuda()
+        self.col = torch.from_numpy(np.ascontiguousarray(col, dtype=np.uint32).view(np.int32)).cuda()
+        self.val = torch.from_numpy(np.ascontiguousarray(val_canonical, dtype=np.uint8).reshape(-1)).cuda()
+        if self.val.numel():
+            _capi.check(_capi.lib().lurk_convert_dev(field_id, C.c_void_p(self.val.data_ptr()), self.val.numel() // 32, _capi.FMT_MONTGOMERY,
+                                                     C.c_void_p(self.val.data_ptr()), None))
+
+    def mv(self, field_id, d_z_ptr, d_y_ptr):
+        _capi.check(_capi.lib().lurk_spmv_csr_dev(field_id, C.c_void_p(self.rp.data_ptr()), C.c_void_p(self.col.data_ptr()), C.c_void_p(self.val.data_ptr()),
+                                                  self.rows, C.c_void_p(d_z_ptr), C.c_void_p(d_y_ptr), None))
+
+
+def padded_and_transposed(mats, n_w, num_vars, rows_pad):
+    """host-side set-up (once per circuit shape): columns re-based onto the padded z = (W | 0.. | u | X | 0..) of length 2 num_vars, and the
+    transposes (for compute_eval_table_sparse: sum_row eq(rx)[row] M[row][col]) as CSR over 2 num_vars rows.  mats: [(row_ptr, col, val bytes)]"""
+    fwd, tr = [], []
+    for rp, col, val in mats:
+        rp = np.asarray(rp, dtype=np.uint64)
+        col = np.asarray(col, dtype=np.int64)
+        colm = np.where(col < n_w, col, num_vars + (col - n_w))
+        val = np.ascontiguousarray(val, dtype=np.uint8).reshape(-1, 32)
+        nrows = len(rp) - 1
+        fwd.append((nrows, rp, colm.astype(np.uint32), val.reshape(-1)))
+        row_of = np.repeat(np.arange(nrows, dtype=np.int64), np.diff(rp.astype(np.int64)))
+        order = np.argsort(colm, kind="stable")
+        trp = np.concatenate([[0], np.cumsum(np.bincount(colm, minlength=2 * num_vars))]).astype(np.uint64)
+        tr.append((2 * num_vars, trp, row_of[order].astype(np.uint32), val[order].reshape(-1)))
+    return fwd, tr
+
+
+class RelaxedR1CSProver:
+    """Control flow of Arecibo's spartan::snark::RelaxedR1CSSNARK::prove (reached from `compress`, reference src/proof/nova.rs:341-356) over the
+    C-ABI primitives, every vector device-resident: multiply_vec (SpMV x3), EqPolynomial::evals, the outer (cubic) and inner (quadratic)
+    sum-checks, compute_eval_table_sparse (transposed SpMV x3 + AXPY x2) and the evaluation claims.  The Fiat-Shamir transcript is a
+    callable `challenge(label, data) -> int`; the polynomial-commitment openings (hyperkzg_prove / ipa_prove) are separate calls."""
+
+    def __init__(self, field_id, mats, n_w, n_x):
+        self.field = field_id
+        self.p = int.from_bytes(field_modulus(field_id), "little")
+        self.n_w, self.n_x = n_w, n_x
+        self.rows = len(mats[0][0]) - 1
+        self.log_rows = max(1, (self.rows - 1).bit_length())
+        self.num_vars = 1 << max(1, (max(n_w, n_x + 1) - 1).bit_length())
+        fwd, tr = padded_and_transposed(mats, n_w, self.num_vars, 1 << self.log_rows)
+        self.M = [DeviceCSR(field_id, *m) for m in fwd]
+        self.MT = [DeviceCSR(field_id, *m) for m in tr]
+
+    def _mont(self, x):
+        return _fe(int(x) * (1 << 256) % self.p)
+
+    def _axpy(self, a, b, r, out):
+        _capi.check(_capi.lib().lurk_axpy_dev(self.field, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), _capi.np_ptr(self._mont(r)), a.numel() // 32,
+                                              C.c_void_p(out.data_ptr()), None))
+
+    def pad_z(self, d_W, u, X):
+        """(W | 0.. | u | X | 0..), Montgomery, 2 num_vars elements; d_W: device tensor of n_w Montgomery elements"""
+        import torch
+        z = torch.zeros(2 * self.num_vars * 32, dtype=torch.uint8, device="cuda")
+        z[:self.n_w * 32] = d_W[:self.n_w * 32]
+        tail = np.concatenate([self._mont(u)] + [self._mont(x) for x in X])
+        z[self.num_vars * 32:self.num_vars * 32 + tail.size] = torch.from_numpy(tail).cuda()
+        return z
+
+    def prove(self, d_z, d_E, u, challenge, timings=None):
+        """d_z: padded z (pad_z); d_E: device tensor of `rows` Montgomery elements.  Returns the transcript the verifier needs plus the points
+        (rx, ry) at which E and W have to be opened."""
+        import time
+        import torch
+        f, p, s, nv = self.field, self.p, self.log_rows, self.num_vars
+        n_rows_pad = 1 << s
+        t = time.perf_counter
+
+        def mark(name, t0):
+            if timings is not None:
+                torch.cuda.synchronize()
+                timings[name] = timings.get(name, 0.0) + (t() - t0) * 1e3
+
+        t0 = t()
+        Az, Bz, Cz = (torch.zeros(n_rows_pad * 32, dtype=torch.uint8, device="cuda") for _ in range(3))
+        for M, y in zip(self.M, (Az, Bz, Cz)):
+            M.mv(f, d_z.data_ptr(), y.data_ptr())
+        E = torch.zeros(n_rows_pad * 32, dtype=torch.uint8, device="cuda")
+        E[:self.rows * 32] = d_E[:self.rows * 32]
+        uCzE = torch.empty_like(E)
+        self._axpy(E, Cz, u, uCzE)
+        mark("multiply_vec + u Cz + E", t0)
+        t0 = t()
+        tau = [challenge("tau", i) % p for i in range(s)]
+        eq_tau = torch.empty(n_rows_pad * 32, dtype=torch.uint8, device="cuda")
+        eq_evals(f, tau, eq_tau.data_ptr())
+        mark("eq(tau)", t0)
+        t0 = t()
+        work = [eq_tau, Az.clone(), Bz.clone(), uCzE]
+        outer_rounds, rx, fin = sumcheck_prove(f, CUBIC, [w.data_ptr() for w in work], s, 0,
+                                               lambda rnd, msg: challenge("outer", (rnd, _ints(np.frombuffer(msg, dtype=np.uint8)))))
+        mark("outer sum-check", t0)
+        t0 = t()
+        eq_rx = torch.empty(n_rows_pad * 32, dtype=torch.uint8, device="cuda")
+        eq_evals(f, rx, eq_rx.data_ptr())
+        claims = (fin[1], fin[2], inner_product(f, Cz.data_ptr(), eq_rx.data_ptr(), n_rows_pad), inner_product(f, E.data_ptr(), eq_rx.data_ptr(), n_rows_pad))
+        mark("claims at rx", t0)
+        t0 = t()
+        r = challenge("inner_r", claims) % p
+        ys = [torch.empty(2 * nv * 32, dtype=torch.uint8, device="cuda") for _ in range(3)]
+        for M, y in zip(self.MT, ys):
+            M.mv(f, eq_rx.data_ptr(), y.data_ptr())
+        abc = torch.empty_like(ys[0])
+        self._axpy(ys[0], ys[1], r, abc)
+        self._axpy(abc, ys[2], r * r % p, abc)
+        mark("eval table (transposed SpMV)", t0)
+        t0 = t()
+        joint = (claims[0] + r * claims[1] + r * r * claims[2]) % p
+        zc = d_z.clone()
+        inner_rounds, ry, fin2 = sumcheck_prove(f, QUAD, [abc.data_ptr(), zc.data_ptr()], nv.bit_length(), joint,
+                                                lambda rnd, msg: challenge("inner", (rnd, _ints(np.frombuffer(msg, dtype=np.uint8)))))
+        mark("inner sum-check", t0)
+        t0 = t()
+        eq_ry = torch.empty(nv * 32, dtype=torch.uint8, device="cuda")
+        eq_evals(f, ry[1:], eq_ry.data_ptr())
+        eval_W = inner_product(f, d_z.data_ptr(), eq_ry.data_ptr(), nv)
+        mark("eval W", t0)
+        return dict(outer_rounds=outer_rounds, inner_rounds=inner_rounds, claims=claims, eval_W=eval_W, rx=rx, ry=ry, E_padded=E)
