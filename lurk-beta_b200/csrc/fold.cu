@@ -6,6 +6,7 @@
 // written as grid-stride loops over 32-byte elements with 128-bit loads/stores, one element per thread per
 // iteration (a warp touches 1 KiB contiguous per array), grid = a multiple of the SM count.
 #include "common.cuh"
+#include "reduce.cuh"
 
 #include <initializer_list>
 
@@ -81,14 +82,46 @@ __global__ void __launch_bounds__(256) axpy_kernel(const F *a, const F *__restri
 }
 
 // CSR sparse matrix-vector product, one row per thread (R1CS rows carry a handful of non-zeros)
+// Rows longer than SPMV_LONG non-zeros are not walked by one thread (a transposed R1CS matrix has a few such rows: the columns of u and
+// of the public IO collect one entry per linear constraint -- 10^4..10^5 entries, 11 ms of one thread's time each): the thread that meets
+// one appends it to a list and a second kernel gives every listed row a whole CTA.
+constexpr uint64_t SPMV_LONG = 1024;
 template <class F>
 __global__ void __launch_bounds__(256) spmv_kernel(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
-                                                   const F *__restrict__ val, size_t rows, const F *__restrict__ z, F *__restrict__ y) {
+                                                   const F *__restrict__ val, size_t rows, const F *__restrict__ z, F *__restrict__ y,
+                                                   unsigned *long_count, uint32_t *long_rows, unsigned long_cap) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (size_t)gridDim.x * blockDim.x) {
         uint64_t k0 = row_ptr[i], k1 = row_ptr[i + 1];
+        if (long_rows && k1 - k0 > SPMV_LONG) {
+            const unsigned slot = atomicAdd(long_count, 1u);
+            if (slot < long_cap) { long_rows[slot] = (uint32_t)i; continue; }      // list full: fall through and walk the row here
+        }
         F acc = F::zero();
         for (uint64_t k = k0; k < k1; k++) acc = acc + load_fe<F>(val + k) * load_fe<F>(z + col[k]);
         store_fe(y + i, acc);
+    }
+}
+template <class F>
+__global__ void __launch_bounds__(256) spmv_long_kernel(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col, const F *__restrict__ val,
+                                                        const F *__restrict__ z, F *__restrict__ y, const unsigned *__restrict__ long_count,
+                                                        const uint32_t *__restrict__ long_rows, unsigned long_cap) {
+    __shared__ F sh[8];
+    const unsigned n = *long_count < long_cap ? *long_count : long_cap;
+    for (unsigned r = blockIdx.x; r < n; r += gridDim.x) {
+        const size_t i = long_rows[r];
+        const uint64_t k0 = row_ptr[i], k1 = row_ptr[i + 1];
+        F acc = F::zero();
+        for (uint64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) acc = acc + load_fe<F>(val + k) * load_fe<F>(z + col[k]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc = acc + shfl_down_fe(acc, off);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            F t = sh[0];
+            for (int w = 1; w < 8; w++) t = t + sh[w];
+            store_fe(y + i, t);
+        }
+        __syncthreads();
     }
 }
 
@@ -164,8 +197,21 @@ int lurk_spmv_csr_dev(int field_id, const void *d_row_ptr, const void *d_col, co
     if (rows == 0) return LURK_OK;
     return dispatch_field(field_id, [&](auto f) {
         using F = decltype(f);
-        spmv_kernel<F><<<stream_grid(rows, 256, 8), 256, 0, (cudaStream_t)stream>>>((const uint64_t *)d_row_ptr, (const uint32_t *)d_col,
-                                                                                   (const F *)d_val, rows, (const F *)d_z, (F *)d_y);
+        cudaStream_t s = (cudaStream_t)stream;
+        // stream-ordered scratch for the list of long rows (counter + up to LONG_CAP row indices)
+        constexpr unsigned LONG_CAP = 4096;
+        unsigned *d_long = nullptr;
+        LURK_CUDA_TRY(cudaMallocAsync(&d_long, sizeof(unsigned) * (LONG_CAP + 1), s));
+        cudaError_t e = cudaMemsetAsync(d_long, 0, sizeof(unsigned), s);
+        if (e == cudaSuccess) {
+            spmv_kernel<F><<<stream_grid(rows, 256, 8), 256, 0, s>>>((const uint64_t *)d_row_ptr, (const uint32_t *)d_col, (const F *)d_val, rows,
+                                                                     (const F *)d_z, (F *)d_y, d_long, d_long + 1, LONG_CAP);
+            spmv_long_kernel<F><<<64, 256, 0, s>>>((const uint64_t *)d_row_ptr, (const uint32_t *)d_col, (const F *)d_val, (const F *)d_z, (F *)d_y, d_long,
+                                                    d_long + 1, LONG_CAP);
+            e = cudaGetLastError();
+        }
+        cudaFreeAsync(d_long, s);
+        LURK_CUDA_TRY(e);
         LURK_CUDA_TRY(cudaGetLastError());
         return LURK_OK;
     });

@@ -263,7 +263,7 @@ class RelaxedR1CSProver:
         t0 = t()
         work = [eq_tau, Az.clone(), Bz.clone(), uCzE]
         outer_rounds, rx, fin = sumcheck_prove(f, CUBIC, [w.data_ptr() for w in work], s, 0,
-                                               lambda rnd, msg: challenge("outer", (rnd, _ints(np.frombuffer(msg, dtype=np.uint8)))))
+                                               lambda rnd, msg: challenge("outer", (rnd, _ints(np.frombuffer(msg, dtype=np.uint8)))) % p)
         mark("outer sum-check", t0)
         t0 = t()
         eq_rx = torch.empty(n_rows_pad * 32, dtype=torch.uint8, device="cuda")
@@ -283,7 +283,7 @@ class RelaxedR1CSProver:
         joint = (claims[0] + r * claims[1] + r * r * claims[2]) % p
         zc = d_z.clone()
         inner_rounds, ry, fin2 = sumcheck_prove(f, QUAD, [abc.data_ptr(), zc.data_ptr()], nv.bit_length(), joint,
-                                                lambda rnd, msg: challenge("inner", (rnd, _ints(np.frombuffer(msg, dtype=np.uint8)))))
+                                                lambda rnd, msg: challenge("inner", (rnd, _ints(np.frombuffer(msg, dtype=np.uint8)))) % p)
         mark("inner sum-check", t0)
         t0 = t()
         eq_ry = torch.empty(nv * 32, dtype=torch.uint8, device="cuda")

@@ -106,3 +106,26 @@ def test_compress_chain_is_accepted_by_the_verifier(L, oracle, spec):
     # and a transcript replayed against another instance (u changed) is rejected as well
     assert not ospartan.verify(rows_lists, n_w, prover.num_vars, prover.log_rows, (o.u + 1) % p, o.X, proof, challenge, p)[0]
     assert set(timings) >= {"outer sum-check", "inner sum-check"}
+
+
+def test_spmv_with_very_long_rows(L, oracle, spec):
+    """the transposed R1CS matrices have a few rows with 10^4..10^5 entries (the columns of u and X): lurk_spmv_csr_dev hands rows
+    longer than 1024 non-zeros to whole CTAs; result equals the oracle's SpMV"""
+    import ctypes as C
+    import torch
+    from util import random_elements
+    rng = np.random.default_rng(3)
+    ncols = 3000
+    lens = [2, 0, 5000, 1, 1024, 1025, 3, 70000, 0, 2]
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    col = rng.integers(0, ncols, size=int(rp[-1])).astype(np.uint32)
+    val = random_elements(FIELD, int(rp[-1]), seed=1)
+    zv = random_elements(FIELD, ncols, seed=2)
+    want = oracle.spmv(FIELD, rp, col, val, zv, nthreads=4)
+    M = L.spartan.DeviceCSR(FIELD, len(lens), rp, col, val)
+    dz = to_device(L, FIELD, zv)
+    y = torch.zeros(len(lens) * 32, dtype=torch.uint8, device="cuda")
+    M.mv(FIELD, dz.data_ptr(), y.data_ptr())
+    L._capi.check(L._capi.lib().lurk_convert_dev(FIELD, C.c_void_p(y.data_ptr()), len(lens), L.FMT_CANONICAL, C.c_void_p(y.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), want)
