@@ -751,7 +751,11 @@ int msm_launch(lurk_msm_ctx *ctx, const void *d_scalars, size_t n, int fmt, cuda
         else LURK_CUDA_TRY(cudaMemsetAsync(S.result.p, 0, sizeof(Pt), s));     // all-zero XYZZ = identity
         return LURK_OK;
     }
-    const bool fixed = ctx->d_table != nullptr;
+    // The fixed-base table pays when the shared bucket set is well filled; a SHORT scalar vector under a big key (the fold chain of a
+    // HyperKZG opening: n/2, n/4, ... terms under a 2^21-point key) would spend its time reducing 2^(c-1) nearly empty buckets, so it
+    // takes the plain windowed path on the same bases instead (results are identical).  Device-resident results keep the table.
+    const bool table_pays = !readback || n * (size_t)(Fs::Params::NBITS / std::max(ctx->fixed_c, 1) + 1) >= ((size_t)8 << (std::max(ctx->fixed_c, 1) - 1));
+    const bool fixed = ctx->d_table != nullptr && table_pays;
     if (!readback && !fixed) { set_error("device-resident results need the fixed-base table (lurk_msm_ctx_precompute)"); return LURK_ERR_ARG; }
     MsmPlan P = make_plan(n, Fs::Params::NBITS, fixed ? ctx->fixed_c : 0);
     // sorted-entry offsets are 32-bit: one launch handles < 2^32 (scalar, window) pairs; larger keys are sharded
