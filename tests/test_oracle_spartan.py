@@ -51,3 +51,22 @@ def test_verifier_accepts_folded_instance_and_rejects_tampering(oracle, spec):
     assert not osp.verify(R, n_w, nv, s, (o.u + 1) % p, o.X, good, challenge, p)[0]
     lie = dict(good, eval_W=(good["eval_W"] + 1) % p)
     assert not osp.verify(R, n_w, nv, s, o.u, o.X, lie, challenge, p)[0]
+
+
+def test_host_setup_of_padded_and_transposed_matrices(spec):
+    """lurk-beta_b200/spartan.py: padded_and_transposed (numpy, no GPU): the re-based columns follow oracle col_map and the transposed CSR
+    holds exactly the entries of the forward one"""
+    import lurk_beta_b200 as L
+    from oracle import nifs
+    rng = np.random.default_rng(4)
+    mats, n_w, _ = nifs.synthetic_step_circuit(rng, 2, 6, 3, 3)
+    nv = 1 << max(1, (max(n_w, 3) - 1).bit_length())
+    fwd, tr = L.spartan.padded_and_transposed(mats, n_w, nv, 64)
+    for (rp, col, val), (nrows, frp, fcol, fval), (trows, trp, tcol, tval) in zip(mats, fwd, tr):
+        assert nrows == len(rp) - 1 and trows == 2 * nv and int(trp[-1]) == int(rp[-1]) == len(fcol)
+        assert [int(c) for c in fcol] == [osp.col_map(int(c), n_w, nv) for c in col]
+        v = ints(val)
+        entries = sorted((i, int(fcol[k]), v[k]) for i in range(nrows) for k in range(int(rp[i]), int(rp[i + 1])))
+        tv = ints(tval)
+        t_entries = sorted((int(tcol[k]), j, tv[k]) for j in range(trows) for k in range(int(trp[j]), int(trp[j + 1])))
+        assert entries == t_entries
