@@ -196,3 +196,24 @@ def ntt(field_id, data, inverse=False, nthreads=1):
         zero = np.zeros_like(data)
         data = axpy(field_id, zero, data, ninv, nthreads)
     return data
+
+
+def from_label(curve_id, label, n, nthreads=1):
+    """C port of DlogGroup::from_label (oracle.c: oracle_hash_to_curve_batch) -- the CPU baseline of the N3 row; the curve constants are
+    the ones oracle/h2c.py computes / derives.  Returns n * 64 bytes (affine x | y canonical, identity = zeros)."""
+    import hashlib
+    from . import h2c
+    p = h2c.base_modulus(curve_id)
+    if h2c.CURVE_H2C_METHOD[curve_id] == "SVDW":
+        method, consts = 0, [h2c.curve_b(curve_id), h2c.SVDW_Z % p, *h2c.svdw_constants(curve_id)]
+    else:
+        method, consts = 1, [h2c.curve_b(curve_id), h2c.SSWU_Z % p, h2c.ISO_A[curve_id], h2c.ISO_B, *h2c.isogeny_constants(curve_id)]
+    cb = fes_to_bytes(consts)
+    dst = np.frombuffer(h2c.dst_prime(curve_id, "from_uniform_bytes"), dtype=np.uint8).copy()
+    msgs = np.frombuffer(hashlib.shake_256(bytes(label)).digest(32 * n), dtype=np.uint8).copy() if n else np.zeros(1, dtype=np.uint8)
+    out = np.zeros(64 * n, dtype=np.uint8)
+    rc = lib().oracle_hash_to_curve_batch(curve_id, method, _ptr(cb), _ptr(dst), C.c_size_t(dst.size), _ptr(msgs), C.c_size_t(32), C.c_size_t(n), _ptr(out),
+                                          nthreads)
+    if rc:
+        raise ValueError(f"oracle_hash_to_curve_batch rc={rc}")
+    return out

@@ -686,6 +686,219 @@ int oracle_ntt(int field_id, uint8_t *data, int log_n, const uint8_t root[32], i
     return 0;
 }
 
+/* ------------------------------------------------------------------ N3: from_label / hash_to_curve (CPU port) */
+/* Restates oracle/h2c.py in C (BLAKE2b-XMD hash_to_field, SVDW or SSWU + 3-isogeny, affine sum): the CPU baseline of the N3 row and a
+ * third implementation beside the Python restatement and the CUDA templates.  Every curve constant arrives from the caller
+ * (oracle/capi.py passes what oracle/h2c.py computes / derives): consts = canonical 32-byte elements,
+ *   method 0 (SVDW):  b, Z, c1, c2, c3, c4            method 1 (SSWU): b, Z, iso_a, iso_b, iso[0..12] */
+static const uint64_t B2B_IV[8] = {0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull, 0xa54ff53a5f1d36f1ull,
+                                   0x510e527fade682d1ull, 0x9b05688c2b3e6c1full, 0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull};
+static const uint8_t B2B_SIGMA[12][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0},
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3}};
+static inline uint64_t rotr64(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+static void b2b_compress(uint64_t h[8], const uint8_t block[128], uint64_t t, int last) {
+    uint64_t m[16], v[16];
+    memcpy(m, block, 128);
+    for (int i = 0; i < 8; i++) { v[i] = h[i]; v[i + 8] = B2B_IV[i]; }
+    v[12] ^= t;
+    if (last) v[14] = ~v[14];
+#define B2B_G(a, b, c, d, x, y) \
+    v[a] += v[b] + (x); v[d] = rotr64(v[d] ^ v[a], 32); v[c] += v[d]; v[b] = rotr64(v[b] ^ v[c], 24); \
+    v[a] += v[b] + (y); v[d] = rotr64(v[d] ^ v[a], 16); v[c] += v[d]; v[b] = rotr64(v[b] ^ v[c], 63);
+    for (int r = 0; r < 12; r++) {
+        const uint8_t *s = B2B_SIGMA[r];
+        B2B_G(0, 4, 8, 12, m[s[0]], m[s[1]]) B2B_G(1, 5, 9, 13, m[s[2]], m[s[3]]) B2B_G(2, 6, 10, 14, m[s[4]], m[s[5]]) B2B_G(3, 7, 11, 15, m[s[6]], m[s[7]])
+        B2B_G(0, 5, 10, 15, m[s[8]], m[s[9]]) B2B_G(1, 6, 11, 12, m[s[10]], m[s[11]]) B2B_G(2, 7, 8, 13, m[s[12]], m[s[13]]) B2B_G(3, 4, 9, 14, m[s[14]], m[s[15]])
+    }
+#undef B2B_G
+    for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[i + 8];
+}
+/* BLAKE2b-512 of a message of at most 256 bytes */
+static void b2b_512(const uint8_t *msg, size_t len, uint8_t out[64]) {
+    uint64_t h[8];
+    uint8_t blk[128];
+    for (int i = 0; i < 8; i++) h[i] = B2B_IV[i];
+    h[0] ^= 0x01010040ull;
+    size_t off = 0;
+    while (len - off > 128) { b2b_compress(h, msg + off, off + 128, 0); off += 128; }
+    memset(blk, 0, 128);
+    memcpy(blk, msg + off, len - off);
+    b2b_compress(h, blk, len, 1);
+    memcpy(out, h, 64);
+}
+/* 64 big-endian bytes -> field element (Montgomery): (hi 2^256 + lo) mod p */
+static void fe_from_be64(const fctx *f, fe *r, const uint8_t d[64]) {
+    uint64_t lo[4], hi[4];
+    for (int w = 0; w < 4; w++) {
+        uint64_t l = 0, h = 0;
+        for (int b = 0; b < 8; b++) { l |= (uint64_t)d[63 - 8 * w - b] << (8 * b); h |= (uint64_t)d[31 - 8 * w - b] << (8 * b); }
+        lo[w] = l; hi[w] = h;
+    }
+    while (ge(lo, f->p)) sub_n(lo, lo, f->p);
+    while (ge(hi, f->p)) sub_n(hi, hi, f->p);
+    fe lm, hm;
+    f_from_raw(f, &lm, lo);
+    f_from_raw(f, &hm, hi);
+    f_mul(f, &hm, &hm, &f->r2);        /* times 2^256 */
+    f_add(f, r, &lm, &hm);
+}
+typedef struct { int s; uint64_t t[4], t1h[4]; fe c; } sqrt_ctx;     /* p - 1 = 2^s t; t1h = (t + 1) / 2; c = z^t, z a non-square */
+static void sqrt_init(const fctx *f, sqrt_ctx *q) {
+    uint64_t one[4] = {1, 0, 0, 0}, pm1[4], half[4];
+    sub_n(pm1, f->p, one);
+    memcpy(q->t, pm1, 32);
+    q->s = 0;
+    while (!(q->t[0] & 1)) { for (int i = 0; i < 3; i++) q->t[i] = (q->t[i] >> 1) | (q->t[i + 1] << 63); q->t[3] >>= 1; q->s++; }
+    add_n(q->t1h, q->t, one);
+    for (int i = 0; i < 3; i++) q->t1h[i] = (q->t1h[i] >> 1) | (q->t1h[i + 1] << 63);
+    q->t1h[3] >>= 1;
+    memcpy(half, pm1, 32);
+    for (int i = 0; i < 3; i++) half[i] = (half[i] >> 1) | (half[i + 1] << 63);
+    half[3] >>= 1;
+    for (uint64_t z = 2;; z++) {
+        uint64_t raw[4] = {z, 0, 0, 0};
+        fe zm, e;
+        f_from_raw(f, &zm, raw);
+        f_pow(f, &e, &zm, half);
+        if (!f_eq(&e, &f->r)) { f_pow(f, &q->c, &zm, q->t); break; }
+    }
+}
+/* returns 1 and a square root when x is a square (Tonelli-Shanks), 0 otherwise */
+static int f_sqrt(const fctx *f, const sqrt_ctx *q, fe *r, const fe *x) {
+    if (f_is_zero(x)) { *r = *x; return 1; }
+    fe c = q->c, rr, tt;
+    f_pow(f, &rr, x, q->t1h);
+    f_pow(f, &tt, x, q->t);
+    int m = q->s;
+    while (!f_eq(&tt, &f->r)) {
+        int i = 0;
+        fe x2 = tt;
+        while (!f_eq(&x2, &f->r)) { f_sqr(f, &x2, &x2); i++; if (i == m) return 0; }
+        fe b = c;
+        for (int k = 0; k < m - i - 1; k++) f_sqr(f, &b, &b);
+        f_mul(f, &rr, &rr, &b);
+        f_sqr(f, &c, &b);
+        f_mul(f, &tt, &tt, &c);
+        m = i;
+    }
+    *r = rr;
+    return 1;
+}
+static int f_parity(const fctx *f, const fe *a) { uint64_t raw[4]; f_to_raw(f, raw, a); return (int)(raw[0] & 1); }
+static void curve_rhs(const fctx *f, fe *r, const fe *x, const fe *a, const fe *b) {
+    fe t;
+    f_sqr(f, &t, x); f_add(f, &t, &t, a); f_mul(f, &t, &t, x); f_add(f, r, &t, b);
+}
+/* affine chord-and-tangent on y^2 = x^3 + a x + b; returns 0 for the identity */
+static int aff_add(const fctx *f, fe *x3, fe *y3, const fe *x1, const fe *y1, const fe *x2, const fe *y2, const fe *a) {
+    fe lam, num, den, t;
+    if (f_eq(x1, x2)) {
+        f_add(f, &t, y1, y2);
+        if (f_is_zero(&t)) return 0;
+        f_sqr(f, &num, x1); f_add(f, &t, &num, &num); f_add(f, &num, &t, &num); f_add(f, &num, &num, a);
+        f_add(f, &den, y1, y1);
+    } else { f_sub(f, &num, y2, y1); f_sub(f, &den, x2, x1); }
+    f_inv(f, &den, &den);
+    f_mul(f, &lam, &num, &den);
+    f_sqr(f, &t, &lam); f_sub(f, &t, &t, x1); f_sub(f, x3, &t, x2);
+    f_sub(f, &t, x1, x3); f_mul(f, &t, &lam, &t); f_sub(f, y3, &t, y1);
+    return 1;
+}
+int oracle_hash_to_curve_batch(int curve_id, int method, const uint8_t *consts, const uint8_t *dst_prime, size_t dst_len, const uint8_t *msgs,
+                               size_t msg_len, size_t n, uint8_t *out, int nthreads) {
+    init_fields();
+    if (curve_id < 0 || curve_id > 3 || dst_len > 120 || msg_len > 100) return -1;
+    const fctx *f = &F[CURVE_BASE[curve_id]];
+    const int nc = method == 0 ? 6 : 17;
+    fe K[17];
+    for (int i = 0; i < nc; i++) { uint64_t raw[4]; memcpy(raw, consts + 32 * i, 32); if (!raw_reduced(f, raw)) return -2; f_from_raw(f, &K[i], raw); }
+    sqrt_ctx sq;
+    sqrt_init(f, &sq);
+    fe zero;
+    memset(&zero, 0, sizeof zero);
+    fe nb_over_a, b_over_za;
+    if (method == 1) {
+        fe ia, iz;
+        f_inv(f, &ia, &K[2]); f_mul(f, &nb_over_a, &K[3], &ia); f_neg(f, &nb_over_a, &nb_over_a);
+        f_inv(f, &iz, &K[1]); f_mul(f, &b_over_za, &K[3], &ia); f_mul(f, &b_over_za, &b_over_za, &iz);
+    }
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 0 ? nthreads : 1) reduction(| : bad)
+    for (long long idx = 0; idx < (long long)n; idx++) {
+        const uint8_t *msg = msgs + (size_t)idx * msg_len;
+        uint8_t buf[400], b0[64], b1[64], b2[64];
+        size_t len = 0;
+        memset(buf, 0, 128); len = 128;
+        memcpy(buf + len, msg, msg_len); len += msg_len;
+        buf[len++] = 0; buf[len++] = 128; buf[len++] = 0;
+        memcpy(buf + len, dst_prime, dst_len); len += dst_len;
+        b2b_512(buf, len, b0);
+        memcpy(buf, b0, 64); buf[64] = 1; memcpy(buf + 65, dst_prime, dst_len);
+        b2b_512(buf, 65 + dst_len, b1);
+        for (int i = 0; i < 64; i++) buf[i] = b0[i] ^ b1[i];
+        buf[64] = 2;
+        b2b_512(buf, 65 + dst_len, b2);
+        fe u[2], px[2], py[2];
+        fe_from_be64(f, &u[0], b1);
+        fe_from_be64(f, &u[1], b2);
+        for (int k = 0; k < 2; k++) {
+            fe x, y, gx, t;
+            if (method == 0) {                       /* SVDW, RFC 9380 6.6.1 */
+                const fe *b = &K[0], *Z = &K[1], *c1 = &K[2], *c2 = &K[3], *c3 = &K[4], *c4 = &K[5];
+                fe tv1, tv2, tv3, tv4, x1, x2, x3;
+                f_sqr(f, &tv1, &u[k]); f_mul(f, &tv1, &tv1, c1);
+                f_add(f, &tv2, &f->r, &tv1); f_sub(f, &tv1, &f->r, &tv1);
+                f_mul(f, &tv3, &tv1, &tv2); f_inv(f, &tv3, &tv3);
+                f_mul(f, &tv4, &u[k], &tv1); f_mul(f, &tv4, &tv4, &tv3); f_mul(f, &tv4, &tv4, c3);
+                f_sub(f, &x1, c2, &tv4); f_add(f, &x2, c2, &tv4);
+                f_sqr(f, &x3, &tv2); f_mul(f, &x3, &x3, &tv3); f_sqr(f, &x3, &x3); f_mul(f, &x3, &x3, c4); f_add(f, &x3, &x3, Z);
+                curve_rhs(f, &gx, &x1, &zero, b);
+                if (f_sqrt(f, &sq, &y, &gx)) x = x1;
+                else {
+                    curve_rhs(f, &gx, &x2, &zero, b);
+                    if (f_sqrt(f, &sq, &y, &gx)) x = x2;
+                    else { curve_rhs(f, &gx, &x3, &zero, b); if (!f_sqrt(f, &sq, &y, &gx)) bad |= 1; x = x3; }
+                }
+            } else {                                 /* simplified SWU on the isogenous curve, RFC 9380 6.6.2 */
+                const fe *Z = &K[1], *ia = &K[2], *ib = &K[3];
+                fe zu2, ta, tv1, x1;
+                f_sqr(f, &zu2, &u[k]); f_mul(f, &zu2, &zu2, Z);
+                f_sqr(f, &ta, &zu2); f_add(f, &ta, &ta, &zu2);
+                f_inv(f, &tv1, &ta);
+                if (f_is_zero(&tv1)) x1 = b_over_za;
+                else { f_add(f, &t, &f->r, &tv1); f_mul(f, &x1, &nb_over_a, &t); }
+                curve_rhs(f, &gx, &x1, ia, ib);
+                if (f_sqrt(f, &sq, &y, &gx)) x = x1;
+                else { f_mul(f, &x, &zu2, &x1); curve_rhs(f, &gx, &x, ia, ib); if (!f_sqrt(f, &sq, &y, &gx)) bad |= 1; }
+            }
+            if (f_parity(f, &u[k]) != f_parity(f, &y)) f_neg(f, &y, &y);
+            px[k] = x; py[k] = y;
+        }
+        fe rx, ry;
+        int finite = aff_add(f, &rx, &ry, &px[0], &py[0], &px[1], &py[1], method == 0 ? &zero : &K[2]);
+        if (finite && method == 1) {               /* the 3-isogeny onto the target curve */
+            const fe *c = &K[4];
+            fe nx, dx, ny, dy, t;
+            f_mul(f, &nx, &c[0], &rx); f_add(f, &nx, &nx, &c[1]); f_mul(f, &nx, &nx, &rx); f_add(f, &nx, &nx, &c[2]); f_mul(f, &nx, &nx, &rx); f_add(f, &nx, &nx, &c[3]);
+            f_add(f, &dx, &rx, &c[4]); f_mul(f, &dx, &dx, &rx); f_add(f, &dx, &dx, &c[5]);
+            f_mul(f, &ny, &c[6], &rx); f_add(f, &ny, &ny, &c[7]); f_mul(f, &ny, &ny, &rx); f_add(f, &ny, &ny, &c[8]); f_mul(f, &ny, &ny, &rx); f_add(f, &ny, &ny, &c[9]);
+            f_mul(f, &ny, &ny, &ry);
+            f_add(f, &dy, &rx, &c[10]); f_mul(f, &dy, &dy, &rx); f_add(f, &dy, &dy, &c[11]); f_mul(f, &dy, &dy, &rx); f_add(f, &dy, &dy, &c[12]);
+            if (f_is_zero(&dx) || f_is_zero(&dy)) finite = 0;
+            else { f_inv(f, &t, &dx); f_mul(f, &rx, &nx, &t); f_inv(f, &t, &dy); f_mul(f, &ry, &ny, &t); }
+        }
+        uint64_t raw[4];
+        if (!finite) memset(out + 64 * (size_t)idx, 0, 64);
+        else { f_to_raw(f, raw, &rx); memcpy(out + 64 * (size_t)idx, raw, 32); f_to_raw(f, raw, &ry); memcpy(out + 64 * (size_t)idx + 32, raw, 32); }
+    }
+    return bad ? -3 : 0;
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

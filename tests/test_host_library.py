@@ -190,3 +190,34 @@ def test_plain_c_fold_driver_fails_loudly_without_gpu(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "fold_client ok" in out.stdout
+
+
+def test_n3_n4_entry_points_reject_bad_arguments_and_have_no_cpu_fallback(L):
+    """argument validation of the N3 / N4 entry points happens before any device work; with valid arguments and no GPU they fail with
+    LURK_ERR_NOGPU (no CPU fallback anywhere in the product)"""
+    import ctypes as C
+    lib, E = L._capi.lib(), L._capi
+    cb = E.CHALLENGE_FN(lambda user, rnd, msg, n, out: 0)
+    buf = np.zeros(4096, dtype=np.uint8)
+    ptrs = (C.c_void_p * 4)(*[C.c_void_p(buf.ctypes.data)] * 4)       # never dereferenced on these paths
+    nr = (C.c_int * 1)(3)
+    z32 = E.np_ptr(np.zeros(32, dtype=np.uint8))
+    assert lib.lurk_sumcheck_prove_dev(0, 9, ptrs, 3, z32, cb, None, None, None, None, 0, None) == E.ERR_ARG          # unknown kind
+    assert lib.lurk_sumcheck_prove_dev(0, 0, ptrs, 41, z32, cb, None, None, None, None, 0, None) == E.ERR_ARG         # too many rounds
+    assert lib.lurk_sumcheck_prove_dev(0, 0, ptrs, 3, z32, cb, None, None, None, None, 7, None) == E.ERR_ARG          # bad format
+    assert lib.lurk_sumcheck_prove_batch_dev(0, 0, 0, ptrs, nr, z32, None, cb, None, None, None, None, 0, None) == E.ERR_ARG   # no instance
+    assert lib.lurk_sumcheck_prove_batch_dev(0, 0, 61, ptrs, nr, z32, None, cb, None, None, None, None, 0, None) == E.ERR_ARG  # too many
+    assert lib.lurk_eq_evals_dev(0, z32, 33, C.c_void_p(buf.ctypes.data), 0, None) == E.ERR_ARG
+    assert lib.lurk_ipa_fold_scalars_dev(0, C.c_void_p(buf.ctypes.data), 6, z32, z32, 0, None) == E.ERR_ARG             # n not a power of two
+    assert lib.lurk_ipa_fold_bases_dev(0, C.c_void_p(buf.ctypes.data), 1, z32, z32, 0, None) == E.ERR_ARG
+    assert lib.lurk_hyperkzg_prove_dev(0, None, C.c_void_p(buf.ctypes.data), z32, 3, cb, None, None, None, None, 0, None) == E.ERR_ARG
+    assert lib.lurk_ck_powers_dev(0, None, z32, 4, C.c_void_p(buf.ctypes.data), 0, None) == E.ERR_ARG
+    assert lib.lurk_ck_generate_range_dev(9, b"ck", 2, 0, 4, C.c_void_p(buf.ctypes.data), None) == E.ERR_ARG            # unknown curve
+    assert lib.lurk_msm_ctx_info(None, None, None) == E.ERR_ARG
+    assert len(lib.lurk_last_error()) > 0
+    if lib.lurk_device_count() == 0:
+        assert lib.lurk_sumcheck_prove_dev(0, 0, ptrs, 3, z32, cb, None, None, None, None, 0, None) == E.ERR_NOGPU
+        assert lib.lurk_eq_evals_dev(0, z32, 1, C.c_void_p(buf.ctypes.data), 0, None) == E.ERR_NOGPU
+        assert lib.lurk_inner_product_dev(0, C.c_void_p(buf.ctypes.data), C.c_void_p(buf.ctypes.data), 4, z32, 0, None) == E.ERR_NOGPU
+        assert lib.lurk_ck_powers_dev(0, E.np_ptr(np.zeros(64, dtype=np.uint8)), z32, 4, C.c_void_p(buf.ctypes.data), 0, None) == E.ERR_NOGPU
+        assert lib.lurk_ck_generate_range_dev(0, b"ck", 2, 0, 4, C.c_void_p(buf.ctypes.data), None) == E.ERR_NOGPU

@@ -174,3 +174,12 @@ def test_library_host_only_entry_points(L):
         with pytest.raises(L.LurkError) as e:
             L.hash_to_curve_batch(0, PREFIX, np.zeros(32, dtype=np.uint8), 32)
         assert e.value.code == L._capi.ERR_NOGPU
+
+
+@pytest.mark.parametrize("curve", [0, 1, 2, 3])
+def test_c_port_of_from_label_equals_python_restatement(oracle, curve):
+    """oracle.c: oracle_hash_to_curve_batch (the CPU baseline of the N3 row) against oracle/h2c.py -- with the host build of the CUDA
+    templates that makes three implementations agreeing point for point"""
+    n = 150
+    assert oracle.from_label(curve, b"ck", n, nthreads=4).tobytes() == h2c.from_label_bytes(curve, b"ck", n)
+    assert oracle.from_label(curve, b"", 3).tobytes() == h2c.from_label_bytes(curve, b"", 3)

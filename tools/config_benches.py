@@ -234,14 +234,20 @@ def ck_generate(logn=21):
         t0 = time.perf_counter()
         hashlib.shake_256(b"ck").digest(32 * n)
         xof = time.perf_counter() - t0
-        from oracle import h2c   # checker / CPU baseline only
+        from oracle import h2c, capi as ocapi   # checker / CPU baseline only
         t0 = time.perf_counter()
         h2c.from_label(curve, b"ck", 256)
         orc = (time.perf_counter() - t0) / 256
+        th = os.cpu_count() or 1
+        nc = 64 * th
+        t0 = time.perf_counter()
+        ocapi.from_label(curve, b"ck", nc, nthreads=th)
+        orc_c = (time.perf_counter() - t0) / nc
         emit(config=f"N3: from_label, 2^{logn} points", curve=cname, n=n, kernel_ms=round(med, 2), mpoints_per_s=round(n / med / 1e3, 2),
              whole_call_ms=round(whole * 1e3, 1), hashlib_xof_ms=round(xof * 1e3, 1), work=exps,
              algorithmic_gb_s=round(n * 96 / med / 1e6, 2), hbm_frac=round(n * 96 / med / 1e6 / PEAK, 5),
-             cpu_oracle_python_us_per_point=round(orc * 1e6, 1), bound="FMA-heavy (IMAD.WIDE) pipe: fixed-exponent exponentiations")
+             cpu_oracle_python_us_per_point=round(orc * 1e6, 1), cpu_port_c_us_per_point_all_threads=round(orc_c * 1e6, 2), cpu_threads=th,
+             cpu_port_c_seconds_for_this_key=round(orc_c * n, 1), bound="FMA-heavy (IMAD.WIDE) pipe: fixed-exponent exponentiations")
 
 
 if __name__ == "__main__":
