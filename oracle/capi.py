@@ -217,3 +217,33 @@ def from_label(curve_id, label, n, nthreads=1):
     if rc:
         raise ValueError(f"oracle_hash_to_curve_batch rc={rc}")
     return out
+
+
+def sumcheck_prove(field_id, kind, polys_bytes, log_n, claim, challenge, nthreads=1):
+    """C port of oracle/sumcheck.py: prove (oracle.c: oracle_sc_*), the CPU baseline of the N4 sum-check rows.
+    polys_bytes: k buffers of 2^log_n canonical elements.  Returns (rounds, challenges, finals) like sumcheck.prove."""
+    from . import sumcheck as sc
+    p = spec.FIELD_MODULUS[field_id]
+    k, E = (2, 2) if kind == "quad" else (4, 3)
+    flat = np.concatenate([np.ascontiguousarray(b, dtype=np.uint8).reshape(-1) for b in polys_bytes])
+    l = lib()
+    l.oracle_sc_new.restype = C.c_void_p
+    h = C.c_void_p(l.oracle_sc_new(field_id, 0 if kind == "quad" else 1, _ptr(flat), C.c_size_t(1 << log_n)))
+    try:
+        rounds, rs = [], []
+        ev = np.zeros(32 * E, dtype=np.uint8)
+        for rnd in range(log_n):
+            l.oracle_sc_round(h, _ptr(ev), nthreads)
+            e = [int.from_bytes(ev[32 * i:32 * i + 32].tobytes(), "little") for i in range(E)]
+            evals = [e[0], (claim - e[0]) % p] + e[1:]
+            r = challenge(rnd, evals) % p
+            rounds.append(evals)
+            rs.append(r)
+            claim = sc.uni_eval_from_evals(evals, r, p)
+            rc = l.oracle_sc_bind(h, _ptr(fes_to_bytes([r])), nthreads)
+            assert rc == 0
+        heads = np.zeros(32 * k, dtype=np.uint8)
+        l.oracle_sc_heads(h, _ptr(heads))
+        return rounds, rs, [int.from_bytes(heads[32 * i:32 * i + 32].tobytes(), "little") for i in range(k)]
+    finally:
+        l.oracle_sc_free(h)

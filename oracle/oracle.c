@@ -899,6 +899,106 @@ int oracle_hash_to_curve_batch(int curve_id, int method, const uint8_t *consts, 
     return bad ? -3 : 0;
 }
 
+/* ------------------------------------------------------------------ N4: sum-check prover rounds (CPU port) */
+/* Restates oracle/sumcheck.py (prove_quad / prove_cubic_with_additive_term of Arecibo's SumcheckProof) on Montgomery arrays with OpenMP:
+ * the CPU baseline of the N4 sum-check rows.  kind 0: A B (2 polynomials), kind 1: A (B C - D) (4 polynomials). */
+typedef struct { int field, kind, k; size_t len; fe *poly[4]; } sc_state;
+void *oracle_sc_new(int field_id, int kind, const uint8_t *polys /* k arrays of len canonical elements, back to back */, size_t len) {
+    init_fields();
+    if (field_id < 0 || field_id > 3 || (kind != 0 && kind != 1)) return NULL;
+    const fctx *f = &F[field_id];
+    sc_state *st = calloc(1, sizeof *st);
+    st->field = field_id; st->kind = kind; st->k = kind == 0 ? 2 : 4; st->len = len;
+    for (int j = 0; j < st->k; j++) {
+        st->poly[j] = malloc(sizeof(fe) * (len ? len : 1));
+        for (size_t i = 0; i < len; i++) { uint64_t raw[4]; memcpy(raw, polys + 32 * ((size_t)j * len + i), 32); f_from_raw(f, &st->poly[j][i], raw); }
+    }
+    return st;
+}
+void oracle_sc_free(void *h) {
+    sc_state *st = h;
+    if (!st) return;
+    for (int j = 0; j < st->k; j++) free(st->poly[j]);
+    free(st);
+}
+/* s(0), s(2)[, s(3)] of the current round, canonical */
+int oracle_sc_round(void *h, uint8_t *evals_out, int nthreads) {
+    sc_state *st = h;
+    const fctx *f = &F[st->field];
+    const size_t half = st->len / 2;
+    const int E = st->kind == 0 ? 2 : 3, K = st->k;
+    if (nthreads < 1) nthreads = 1;
+    fe *part = calloc((size_t)nthreads * 3, sizeof(fe));
+#pragma omp parallel num_threads(nthreads)
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        fe acc[3];
+        memset(acc, 0, sizeof acc);
+#pragma omp for schedule(static)
+        for (long long i = 0; i < (long long)half; i++) {
+            fe lo[4], p2[4], p3[4], d, t;
+            for (int j = 0; j < K; j++) {
+                lo[j] = st->poly[j][i];
+                f_sub(f, &d, &st->poly[j][half + i], &lo[j]);
+                f_add(f, &p2[j], &st->poly[j][half + i], &d);
+                f_add(f, &p3[j], &p2[j], &d);
+            }
+            if (st->kind == 0) {
+                f_mul(f, &t, &lo[0], &lo[1]); f_add(f, &acc[0], &acc[0], &t);
+                f_mul(f, &t, &p2[0], &p2[1]); f_add(f, &acc[1], &acc[1], &t);
+            } else {
+                f_mul(f, &t, &lo[1], &lo[2]); f_sub(f, &t, &t, &lo[3]); f_mul(f, &t, &t, &lo[0]); f_add(f, &acc[0], &acc[0], &t);
+                f_mul(f, &t, &p2[1], &p2[2]); f_sub(f, &t, &t, &p2[3]); f_mul(f, &t, &t, &p2[0]); f_add(f, &acc[1], &acc[1], &t);
+                f_mul(f, &t, &p3[1], &p3[2]); f_sub(f, &t, &t, &p3[3]); f_mul(f, &t, &t, &p3[0]); f_add(f, &acc[2], &acc[2], &t);
+            }
+        }
+        for (int e = 0; e < 3; e++) part[(size_t)tid * 3 + e] = acc[e];
+    }
+    for (int e = 0; e < E; e++) {
+        fe s;
+        memset(&s, 0, sizeof s);
+        for (int t = 0; t < nthreads; t++) f_add(f, &s, &s, &part[(size_t)t * 3 + e]);
+        uint64_t raw[4];
+        f_to_raw(f, raw, &s);
+        memcpy(evals_out + 32 * e, raw, 32);
+    }
+    free(part);
+    return 0;
+}
+/* bind_poly_var_top with the canonical challenge r; the length halves */
+int oracle_sc_bind(void *h, const uint8_t r_bytes[32], int nthreads) {
+    sc_state *st = h;
+    const fctx *f = &F[st->field];
+    uint64_t raw[4];
+    memcpy(raw, r_bytes, 32);
+    if (!raw_reduced(f, raw)) return -2;
+    fe r;
+    f_from_raw(f, &r, raw);
+    const size_t half = st->len / 2;
+    for (int j = 0; j < st->k; j++) {
+        fe *P = st->poly[j];
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+        for (long long i = 0; i < (long long)half; i++) {
+            fe d;
+            f_sub(f, &d, &P[half + i], &P[i]);
+            f_mul(f, &d, &d, &r);
+            f_add(f, &P[i], &P[i], &d);
+        }
+    }
+    st->len = half;
+    return 0;
+}
+/* element 0 of every polynomial, canonical (the final evaluations once the length is 1) */
+int oracle_sc_heads(void *h, uint8_t *out) {
+    sc_state *st = h;
+    const fctx *f = &F[st->field];
+    for (int j = 0; j < st->k; j++) { uint64_t raw[4]; f_to_raw(f, raw, &st->poly[j][0]); memcpy(out + 32 * j, raw, 32); }
+    return 0;
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

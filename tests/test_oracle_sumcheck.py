@@ -157,3 +157,20 @@ def test_oracle_batched_prover_final_check(spec, kind):
     single = sc.prove(insts[0], kind, claims[0], fs_challenge(p, b"b"), p)
     again = sc.prove_batch([insts[0]], kind, [claims[0]], [1], fs_challenge(p, b"b"), p)
     assert (single[0], single[1], single[2]) == (again[0], again[1], again[2][0])
+
+
+@pytest.mark.parametrize("kind", ["quad", "cubic"])
+def test_c_port_of_the_sumcheck_prover_equals_python(oracle, spec, kind):
+    """oracle.c: oracle_sc_* (the CPU baseline of the N4 sum-check rows) against oracle/sumcheck.py, multi-threaded"""
+    import numpy as np
+    from util import ints, random_elements
+    p = spec.FIELD_MODULUS[2]
+    k = 2 if kind == "quad" else 4
+    for l in (0, 1, 7):
+        bufs = [random_elements(2, 1 << l, seed=5 * l + i) for i in range(k)]
+        polys = [ints(b) for b in bufs]
+        comb = sc.comb_quad if kind == "quad" else sc.comb_cubic
+        claim = sum(comb(*[P[i] for P in polys], p) for i in range(1 << l)) % p
+        want = sc.prove(polys, kind, claim, fs_challenge(p, b"c"), p)
+        got = oracle.sumcheck_prove(2, kind, bufs, l, claim, fs_challenge(p, b"c"), nthreads=3)
+        assert (got[0], got[1], got[2]) == (want[0], want[1], want[2])
