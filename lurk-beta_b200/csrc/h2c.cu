@@ -17,7 +17,7 @@ template <class F>
 __global__ void __launch_bounds__(128) h2c_kernel(const __grid_constant__ H2cParams<F> P, const uint8_t *__restrict__ msgs, uint32_t msg_len,
                                                   size_t n, Affine<F> *__restrict__ out, int to_canonical) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        uint8_t m[H2C_MAX_MSG];
+        alignas(16) uint8_t m[H2C_MAX_MSG];      // the 16-byte copies below need it
         const uint8_t *src = msgs + i * msg_len;
         if ((msg_len & 15u) == 0 && (reinterpret_cast<uintptr_t>(msgs) & 15u) == 0) {
             for (uint32_t k = 0; k < msg_len; k += 16) *reinterpret_cast<uint4 *>(m + k) = *reinterpret_cast<const uint4 *>(src + k);
