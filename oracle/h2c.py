@@ -27,7 +27,8 @@ Parity: UNPINNED against Arecibo's actual key (no golden point of the key exists
 Pinned pieces: SHAKE256 and BLAKE2b are Python's hashlib (the CUDA/C++ side has its own implementations, compared with these);
 the group-order and on-curve checks; the isogeny constants.  tests/test_oracle_h2c.py holds those checks.
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this file.
+Only tests/, __graft_entry__.smoke() and the cpu_baseline legs (bench.py; the CPU-timing legs of tools/config_benches.py and
+tools/compress_cpu_baseline.py, where the oracle is the thing timed BESIDE the product, never a checker inside it) may import this file.
 """
 import hashlib
 

@@ -18,7 +18,8 @@ f(beta) g, so the KZG opening identity (beta - u) h(beta) = B(beta) - B(u) and t
 P_{i+1}(u^2)-style checks of the verifier can be evaluated in the field -- `verify_known_beta` below does the verifier's algebra
 without pairings.
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this file.
+Only tests/, __graft_entry__.smoke() and the cpu_baseline legs (bench.py; the CPU-timing legs of tools/config_benches.py and
+tools/compress_cpu_baseline.py, where the oracle is the thing timed BESIDE the product, never a checker inside it) may import this file.
 """
 from . import spec
 

@@ -13,7 +13,8 @@ spartan::snark::RelaxedR1CSSNARK runs it inside `compress` (reference src/proof/
 openings are checked separately (oracle/kzg.py, key of known beta).
 
 Parity: UNPINNED against Arecibo's proof bytes; pinned by construction (the verifier accepts; a perturbed witness is rejected).
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this file.
+Only tests/, __graft_entry__.smoke() and the cpu_baseline legs (bench.py; the CPU-timing legs of tools/config_benches.py and
+tools/compress_cpu_baseline.py, where the oracle is the thing timed BESIDE the product, never a checker inside it) may import this file.
 """
 from . import sumcheck as sc
 

@@ -22,7 +22,8 @@ Parity: UNPINNED against Arecibo's proof bytes (the reference holds no proof fix
 trips).  Pinned by construction instead: the verifier below accepts what the GPU prover produced (round consistency + final
 evaluation against independently evaluated multilinear extensions); the IPA fold keeps <a,b> and the commitment relation.
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this file.
+Only tests/, __graft_entry__.smoke() and the cpu_baseline legs (bench.py; the CPU-timing legs of tools/config_benches.py and
+tools/compress_cpu_baseline.py, where the oracle is the thing timed BESIDE the product, never a checker inside it) may import this file.
 """
 from . import spec
 
