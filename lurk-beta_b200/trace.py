@@ -15,6 +15,10 @@ All integers little-endian; field elements 32 bytes canonical (`PrimeField::to_r
                            u32 len | len x 32 bytes }
   commit file: "LRKC" | u32 version=1 | u32 curve (0 BN254 G1, 1 Grumpkin, 2 Pallas, 3 Vesta) | u32 flags | u32 n |
                n x 64 bytes affine bases (x | y; identity = 0 | 0) | n x 32 bytes scalars | 64 bytes affine result | u8 is_identity
+  key file   : "LRKK" | u32 version=1 | u32 curve | u32 flags | u32 kind (0 = from_label / Pedersen, 1 = powers of tau / KZG) |
+               u32 label_len | label | u32 n | n x 64 bytes affine points -- the head of the reference's commitment key as
+               `CommitmentKey::setup(label, ..)` produced it (SURVEY.md 8(f) N3): pins lurk_ck_generate (kind 0).  For kind 1 the label
+               field holds g (64 bytes) | beta (32 bytes) as the reference's seeded RNG drew them: pins lurk_ck_powers_dev.
 """
 import struct
 from collections import namedtuple
@@ -30,6 +34,7 @@ TRACE_FIELD_TO_ID = {0: 0, 1: 1, 2: 2, 3: 3}
 Slot = namedtuple("Slot", "slot_type is_dummy witness")          # witness: uint8 array, len * 32 bytes
 SlotTrace = namedtuple("SlotTrace", "field_id synthetic slots")
 CommitTrace = namedtuple("CommitTrace", "curve_id synthetic bases scalars result is_identity")
+KeyTrace = namedtuple("KeyTrace", "curve_id synthetic kind label points")     # points: uint8 array, n * 64 bytes
 
 
 def write_slots(path, field_id, slots, synthetic=True):
@@ -89,6 +94,33 @@ def read_commit(path):
     if off + 65 != len(data):
         raise ValueError(f"{path}: trailing bytes")
     return CommitTrace(curve, bool(flags & FLAG_SYNTHETIC), bases, scalars, result, ident)
+
+
+def write_key(path, curve_id, kind, label, points, synthetic=True):
+    points = np.ascontiguousarray(points, dtype=np.uint8).reshape(-1)
+    assert points.size % 64 == 0
+    label = bytes(label)
+    with open(path, "wb") as f:
+        f.write(b"LRKK" + struct.pack("<IIIII", 1, curve_id, FLAG_SYNTHETIC if synthetic else 0, kind, len(label)) + label)
+        f.write(struct.pack("<I", points.size // 64) + points.tobytes())
+
+
+def read_key(path):
+    data = open(path, "rb").read()
+    if data[:4] != b"LRKK":
+        raise ValueError(f"{path}: not a commitment-key trace")
+    version, curve, flags, kind, ll = struct.unpack_from("<IIIII", data, 4)
+    if version != 1 or kind not in (0, 1):
+        raise ValueError(f"{path}: unknown version / kind")
+    off = 24
+    label = data[off:off + ll]
+    off += ll
+    (n,) = struct.unpack_from("<I", data, off)
+    off += 4
+    pts = np.frombuffer(data, dtype=np.uint8, count=64 * n, offset=off).copy()
+    if off + 64 * n != len(data):
+        raise ValueError(f"{path}: trailing bytes")
+    return KeyTrace(curve, bool(flags & FLAG_SYNTHETIC), kind, label, pts)
 
 
 def slot_batches(trace):

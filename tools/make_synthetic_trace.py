@@ -31,4 +31,13 @@ bases = oracle.gen_bases(0, 64)
 sc = random_elements(0, 64, seed=9, shape="witness")
 pt = oracle.msm(0, bases, sc)
 T.write_commit(os.path.join(out, "commit_synthetic_bn254.bin"), 0, bases, sc, pt[:64], not pt[64:].any(), synthetic=True)
+# N3: the head of the commitment key (kind 0 = from_label on Grumpkin, the secondary circuit's Pedersen key; kind 1 = powers of tau on BN254 G1)
+from oracle import h2c, kzg, spec          # noqa: E402
+T.write_key(os.path.join(out, "ck_synthetic_grumpkin.bin"), 1, 0, b"ck", np.frombuffer(h2c.from_label_bytes(1, b"ck", 16), dtype=np.uint8), synthetic=True)
+g = spec.ec_mul(20260924, spec.CURVES[0]["gen"], spec.FIELD_MODULUS[1])
+beta = 0x1b2c3d4e5f60718293a4b5c6d7e8f90a1b2c3d4e5f60718293a4b5c6d7e8f9 % spec.FIELD_MODULUS[0]
+pts = kzg.powers_of_tau(0, g, beta, 12)
+lab = g[0].to_bytes(32, "little") + g[1].to_bytes(32, "little") + beta.to_bytes(32, "little")
+T.write_key(os.path.join(out, "ck_synthetic_kzg_bn254.bin"), 0, 1, lab,
+            np.frombuffer(b"".join(x.to_bytes(32, "little") + y.to_bytes(32, "little") for x, y in pts), dtype=np.uint8), synthetic=True)
 print("wrote", sorted(os.listdir(out)))
