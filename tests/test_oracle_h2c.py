@@ -183,3 +183,19 @@ def test_c_port_of_from_label_equals_python_restatement(oracle, curve):
     n = 150
     assert oracle.from_label(curve, b"ck", n, nthreads=4).tobytes() == h2c.from_label_bytes(curve, b"ck", n)
     assert oracle.from_label(curve, b"", 3).tobytes() == h2c.from_label_bytes(curve, b"", 3)
+
+
+def test_hash_known_answers_independent_of_hashlib(h2clib):
+    """RFC 7693 Appendix A (BLAKE2b-512 of "abc") and the FIPS 202 SHAKE256 empty-message vector, as literals: pins both the product's
+    implementations and the way the oracle drives hashlib (digest size, XOF)"""
+    blake_abc = bytes.fromhex("ba80a53f981c4d0d6a2797b69f12f6e94c212f14685ac4b74b12bb6fdbffa2d1"
+                              "7d87c5392aab792dc252d5de4533cc9518d38aa8dbf1925ab92386edd4009923")
+    shake_empty = bytes.fromhex("46b9dd2b0ba88d13233b3feb743eeb243fcd52ea62b81b82b50c27646ed5762f"
+                                "d75dc4ddd8c0f200cb05019d67b592f6fc821c49479ab48640292eacb3b7c4be")
+    assert hashlib.blake2b(b"abc", digest_size=64).digest() == blake_abc
+    assert hashlib.shake_256(b"").digest(64) == shake_empty
+    out = ctypes.create_string_buffer(64)
+    h2clib.h2c_test_blake2b(b"abc", 3, out)
+    assert out.raw == blake_abc
+    h2clib.h2c_test_shake256(b"", 0, out, 64, 0)
+    assert out.raw == shake_empty
