@@ -216,11 +216,12 @@ int lurk_shake256(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len
  * N4  The data-parallel loops of `compress` (src/proof/nova.rs:341-356, supernova.rs:293-317 -> Arecibo CompressedSNARK::prove ->
  *     spartan::snark::RelaxedR1CSSNARK::prove): sum-check prover rounds over device-resident multilinear polynomials
  *     (SumcheckProof::prove_quad / prove_cubic_with_additive_term: compute_eval_points_* + bind_poly_var_top) and the folding rounds
- *     of the inner-product argument (provider::ipa_pc::InnerProductArgument::prove), plus EqPolynomial::evals and the inner
- *     product behind MultilinearPolynomial::evaluate.  The Fiat-Shamir transcript (Keccak256Transcript) stays on the caller's side:
+ *     of the inner-product argument (provider::ipa_pc::InnerProductArgument::prove), the HyperKZG opening prover
+ *     (provider::hyperkzg::EvaluationEngine::prove), plus EqPolynomial::evals and the inner product behind
+ *     MultilinearPolynomial::evaluate.  The Fiat-Shamir transcript (Keccak256Transcript) stays on the caller's side:
  *     every round passes its message to `challenge` and receives the verifier's challenge.  Polynomials: 2^num_rounds elements,
  *     Montgomery form, index bit (num_rounds - 1) = the first variable (bound first), as in Arecibo's MultilinearPolynomial.
- *     Not here: the transcript, proof (de)serialisation, HyperKZG (pairing side) and the verifier -- CPU / third-party protocol code.
+ *     Not here: the transcript, proof (de)serialisation, the verifiers (HyperKZG's pairing check) -- CPU / third-party protocol code.
  * ------------------------------------------------------------------------------------------------- */
 /* message: the round's prover message in `fmt` -- sum-check: s(0) | s(1) | s(2) [| s(3)] (32 bytes each; Arecibo absorbs the
  * compressed form, i.e. the coefficients without the linear one: the caller converts);  IPA: L | R as 96-byte points.
