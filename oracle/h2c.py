@@ -23,7 +23,10 @@ this file restates their published algorithms:
     pasta_curves ISOGENY_CONSTANTS (first: 0x0e38e38e...aaaaaaab = 1/9, last: p - 540).  iso-curve coefficients `a` are checked by
     the group order (an isogenous curve has the same number of points).
 
-Parity: UNPINNED against Arecibo's actual key (no golden point of the key exists in the reference).
+Parity: the Pasta hash_to_curve is PINNED by pasta_curves' own unit-test vectors (tests/golden/pasta_hash_to_curve_vectors.json: this file
+reproduces hash_to_curve("z.cash:test") of "Trans rights now!" on Pallas and of "hello" on Vesta); the SVDW curves (halo2curves has property
+tests only) and the way Arecibo feeds the SHAKE256 stream into it are UNPINNED against Arecibo's actual key (no golden point of the key exists in
+the reference).
 Pinned pieces: SHAKE256 and BLAKE2b are Python's hashlib (the CUDA/C++ side has its own implementations, compared with these);
 the group-order and on-curve checks; the isogeny constants.  tests/test_oracle_h2c.py holds those checks.
 

@@ -152,3 +152,22 @@ def test_key_slice_of_a_sharded_key(L, curve):
                                                     C.c_void_p(buf.data_ptr()), None))
         torch.cuda.synchronize()
         assert buf.cpu().numpy().tobytes() == whole[64 * first:64 * (first + n)].tobytes(), (first, n)
+
+
+def test_pasta_curves_own_vectors_on_the_gpu(L):
+    """tests/golden/pasta_hash_to_curve_vectors.json (pasta_curves 0.5.0 unit tests) through lurk_hash_to_curve_batch"""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "pasta_hash_to_curve_vectors.json")) as f:
+        vectors = json.load(f)["vectors"]
+    for v in vectors:
+        c, msg = v["curve_id"], v["message_ascii"].encode()
+        p = h2c.base_modulus(c)
+        x, z = int(v["x"], 16), int(v["z"], 16)
+        zi = pow(z, -1, p)
+        got = pts_of(L.hash_to_curve_batch(c, v["domain_prefix"], np.frombuffer(msg, dtype=np.uint8), len(msg)))[0]
+        assert got[0] == x * zi * zi % p
+        if v["y"]:
+            assert got[1] == int(v["y"], 16) * zi * zi * zi % p
+        assert got == h2c.hash_to_curve(c, v["domain_prefix"], msg)

@@ -199,3 +199,32 @@ def test_hash_known_answers_independent_of_hashlib(h2clib):
     assert out.raw == blake_abc
     h2clib.h2c_test_shake256(b"", 0, out, 64, 0)
     assert out.raw == shake_empty
+
+
+def _pasta_vectors():
+    with open(os.path.join(ROOT, "tests", "golden", "pasta_hash_to_curve_vectors.json")) as f:
+        return json.load(f)["vectors"]
+
+
+def _affine_of(v, p):
+    x, z = int(v["x"], 16), int(v["z"], 16)
+    zi = pow(z, -1, p)
+    ax = x * zi * zi % p
+    ay = int(v["y"], 16) * zi * zi * zi % p if v["y"] else None
+    return ax, ay
+
+
+@pytest.mark.parametrize("v", _pasta_vectors(), ids=lambda v: v["curve"])
+def test_pasta_curves_own_hash_to_curve_vectors(h2clib, v):
+    """pasta_curves' unit-test vectors (Jacobian x, y, z of hash_to_curve("z.cash:test")(msg)): the oracle AND the host build of the CUDA
+    templates reproduce them -- the external pin of hash_to_field (BLAKE2b XMD, DST layout), SSWU (Z = -13, iso-curve coefficients, sign rule),
+    the sum on the iso-curve and the 3-isogeny.  This is what makes from_label on Pallas / Vesta 'pinned' rather than 'restated'."""
+    c, msg = v["curve_id"], v["message_ascii"].encode()
+    p, b = h2c.base_modulus(c), h2c.curve_b(c)
+    ax, ay = _affine_of(v, p)
+    got = h2c.hash_to_curve(c, v["domain_prefix"], msg)
+    assert got[0] == ax and (ay is None or got[1] == ay)
+    assert (got[1] ** 2 - got[0] ** 3 - b) % p == 0
+    out = ctypes.create_string_buffer(64)
+    assert h2clib.h2c_test_point(c, v["domain_prefix"].encode(), msg, len(msg), out) == 0
+    assert _pt(out) == got
