@@ -21,7 +21,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, n, curve, ret):
+def _worker(rank, world, port, n, curve, ret, key_kind="synthetic"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
@@ -32,7 +32,8 @@ def _worker(rank, world, port, n, curve, ret):
     from oracle import spec
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
-        bases = oracle.gen_bases(curve, n)
+        # "from_label": the reference's hash-to-curve key (N3), each rank owning the slice lurk_ck_generate_range_dev would generate for it
+        bases = oracle.gen_bases(curve, n) if key_kind == "synthetic" else oracle.from_label(curve, b"ck", n, nthreads=2)
         scalars = random_elements(spec.CURVES[curve]["scalar"], n, seed=99, shape="witness")
         lo, hi = L.shard_bounds(n, world, rank)
         key = ShardedCommitmentKey.__new__(ShardedCommitmentKey)      # no GPU here: skip the device upload
@@ -52,6 +53,15 @@ def test_sharded_commit_combine_world2(n):
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), n, 2, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+def test_sharded_commit_over_a_from_label_key_world2():
+    """the same combine over slices of the hash-to-curve key (oracle's C port stands in for the per-rank GPU generation)"""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), 301, 0, ret, "from_label"), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
 
 
